@@ -1,0 +1,8 @@
+"""TEST INFRASTRUCTURE ONLY: loaders for the CPU oracle (port) and the compiled reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this package.
+Nothing under vif_b200/ does (checked by tests/test_no_oracle_in_product.py).
+"""
+from .oracle import (OracleGrid, have_ref, oracle_qxmatch, oracle_grid, oracle_ring,  # noqa: F401
+                     oracle_field_area_bbox, oracle_angdist, ref_qxmatch, ref_ring,
+                     ref_field_area_bbox, ref_angdist, build, NPOS)
