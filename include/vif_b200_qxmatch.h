@@ -1,0 +1,152 @@
+/*
+ * vif_b200_qxmatch.h -- C ABI of the B200-native replacement for vif::astro::qxmatch.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types. The entry points
+ * are what a binding of the reference's only hot path would need:
+ *
+ *   reference interface replaced                               (file:line under /root/reference)
+ *   ----------------------------------------------------------------------------------------
+ *   qxmatch(ra1, dec1, ra2, dec2, qxmatch_params) -> qxmatch_res   include/vif/astro/qxmatch.hpp:133-616
+ *   struct qxmatch_params {thread,nth,verbose,self,brute_force,no_mirror,linear}      qxmatch.hpp:31-39
+ *   struct qxmatch_res {id (nth,n1) ; d (nth,n1) ; rid (n2) ; rd (n2)}                qxmatch.hpp:8-17
+ *   callers: tools/qxmatch2/qxmatch2.cpp:130,148 ; include/vif/astro/catalog_merge.hpp:195
+ *
+ * The C++ drop-in that sits on top of this ABI (same namespace, same signatures as the reference)
+ * is include/vif_b200/astro/qxmatch.hpp; the Python mirror is vif_b200/qxmatch.py.
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - inputs in degrees (any units when `linear`), outputs in arcsec (input units when `linear`);
+ *   - `id`, `d` are plane-major: neighbour rank k of source i is at [k*n1 + i]  (qxmatch.hpp:157);
+ *   - unmatched slots: id = XM_NPOS, d = NaN (inf when `linear`, or when either catalog is empty:
+ *     qxmatch.hpp:165-167, 609-613);
+ *   - cell-binned path with `self`: rid = XM_NPOS, rd = NaN (reverse pass skipped, qxmatch.hpp:395);
+ *   - `thread` is accepted and ignored (the GPU path has no host worker threads);
+ *   - there is NO CPU fallback: every entry point that computes returns XM_ERR_CUDA when no
+ *     CUDA device / kernel image is usable.
+ *
+ * Errors: the reference prints and calls exit(EXIT_FAILURE) (vif_check, core/error.hpp:330-335).
+ * The ABI returns a non-zero code and writes a message into `errbuf`; the C++ shim turns that back
+ * into print + exit. Calls are synchronous. A context (one per device per process, created lazily)
+ * is protected by a mutex: concurrent calls on the same device are serialised.
+ */
+#ifndef VIF_B200_QXMATCH_H
+#define VIF_B200_QXMATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM_NPOS UINT64_MAX            /* vif::npos, core/typedefs.hpp:13 */
+
+enum {
+    XM_OK = 0,
+    XM_ERR_INVALID_ARG = 1,           /* NULL pointer, n >= 2^32-1, bad flag combination          */
+    XM_ERR_NONFINITE_1 = 2,           /* "first RA and Dec coordinates contain invalid values"    */
+    XM_ERR_NONFINITE_2 = 3,           /* "second RA and Dec coordinates contain invalid values"   */
+    XM_ERR_GRID_TOO_LARGE = 4,        /* nra*ndec exceeds XM_MAX_CELLS (reference would allocate it)*/
+    XM_ERR_CUDA = 5,                  /* CUDA runtime failure or no device: message has details   */
+    XM_ERR_NO_MEMORY = 6
+};
+
+#define XM_MAX_CELLS (1ull << 30)
+
+/* Mirrors vif::astro::qxmatch_params (qxmatch.hpp:31-39) field for field, then GPU extras. */
+typedef struct xm_params {
+    uint64_t thread;                  /* ignored by the GPU path                                   */
+    uint64_t nth;                     /* clamped to >= 1 (qxmatch.hpp:152)                         */
+    uint8_t  verbose;
+    uint8_t  self;
+    uint8_t  brute_force;
+    uint8_t  no_mirror;
+    uint8_t  linear;
+    /* ---- extras (zero-initialise for reference behaviour) ---- */
+    uint8_t  has_bbox1;               /* 1: use bbox1[] as catalog 1's bounding box instead of the  */
+                                      /* box of the rows passed (row-sharded multi-GPU runs must   */
+                                      /* bin with the GLOBAL box of qxmatch.hpp:232-238)           */
+    uint8_t  exact_only;              /* 1: disable the filter kernels, run reference-order maths   */
+                                      /* on every pair (debug / parity triage)                     */
+    uint8_t  reserved0;
+    int32_t  device;                  /* CUDA ordinal; -1 = current device                         */
+    int32_t  reserved1;
+    double   bbox1[4];                /* ra_min, ra_max, dec_min, dec_max                          */
+} xm_params;
+
+/* Grid geometry chosen for the cell-binned path (qxmatch.hpp:232-267), reported for inspection. */
+typedef struct xm_grid {
+    double   rra0, rra1, rdec0, rdec1; /* padded bounds                                            */
+    double   cell_size, dra, ddec;     /* cell size [arcsec], cell widths [deg]                    */
+    uint64_t nra, ndec, nc2;
+    double   area;                     /* hull area of catalog 2's bounding box [deg^2]            */
+} xm_grid;
+
+/* Per-call statistics of the last call made on a device (device-side times from CUDA events). */
+typedef struct xm_stats {
+    xm_grid  grid;
+    double   ms_total;                 /* whole device pipeline                                    */
+    double   ms_bbox, ms_keys, ms_sort, ms_index, ms_forward, ms_reverse, ms_refine;
+    uint64_t launches;                 /* kernels launched by this library during the call         */
+    uint64_t rows_refined_fwd;         /* rows the filter kernel handed to the exact kernel        */
+    uint64_t rows_refined_rev;
+    uint64_t rows_ambiguous;           /* rows whose decisive proxies differ by < 8 ulp            */
+    uint64_t evals_fwd, evals_rev;     /* distance evaluations (filter + exact)                    */
+    uint64_t sin_model;                /* 1 = glibc FMA Taylor model, 2 = non-FMA model            */
+} xm_stats;
+
+/* Library / ABI version string, e.g. "vif_b200_qxmatch 0.1 (sm_100a)". Never fails. */
+const char* xm_version(void);
+
+/* Creates the per-device context (stream, memory pool, libm calibration). Optional: every entry
+ * point calls it lazily. device = -1 -> current. Returns XM_OK or XM_ERR_CUDA. */
+int32_t xm_init(int32_t device, char* errbuf, uint64_t errcap);
+
+/* Releases all contexts and device memory owned by the library. */
+void xm_shutdown(void);
+
+/*
+ * qxmatch on HOST buffers (the reference-facing call; replaces qxmatch.hpp:133-616).
+ *   ra1,dec1: n1 doubles; ra2,dec2: n2 doubles.
+ *   id, d:    max(nth,1)*n1 elements, caller-allocated, fully overwritten.
+ *   rid, rd:  n2 elements, or NULL when params->no_mirror.
+ * Copies inputs H2D, runs the device pipeline, copies results D2H. Blocking.
+ */
+int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1,
+                       const double* ra2, const double* dec2, uint64_t n2,
+                       const xm_params* params,
+                       uint64_t* id, double* d, uint64_t* rid, double* rd,
+                       char* errbuf, uint64_t errcap);
+
+/*
+ * Same, on DEVICE buffers already resident in HBM on params->device (or the current device).
+ * `stream` is a cudaStream_t (NULL = the library's own stream); the call synchronises the stream
+ * twice internally (bounding boxes -> host geometry; refine counts) and once before returning.
+ */
+int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1,
+                       const double* ra2, const double* dec2, uint64_t n2,
+                       const xm_params* params,
+                       uint64_t* id, double* d, uint64_t* rid, double* rd,
+                       void* stream, char* errbuf, uint64_t errcap);
+
+/* Host-only: grid geometry from the two bounding boxes {ra_min,ra_max,dec_min,dec_max}
+ * (restates qxmatch.hpp:232-267 with the host libm so that cell keys match the reference). */
+int32_t xm_grid_from_bbox(const double* bbox1, const double* bbox2, uint64_t n2, uint64_t nth,
+                          int32_t linear, xm_grid* out);
+
+/* Device bounding box + finiteness of one catalog: out = {ra_min,ra_max,dec_min,dec_max},
+ * *nonfinite = count of rows with a NaN/inf coordinate (qxmatch.hpp:146-149, 232-235). */
+int32_t xm_bbox_dev(const double* ra, const double* dec, uint64_t n, int32_t device, void* stream,
+                    double* out, uint64_t* nonfinite, char* errbuf, uint64_t errcap);
+
+/* Statistics of the most recent qxmatch call on `device` (-1 = current). */
+int32_t xm_last_stats(int32_t device, xm_stats* out);
+
+/* Stable LSD radix sort of (key,value) u32 pairs on the device -- the sort the cell index is
+ * built with; exported so tests can check it in isolation. key_bits in [1,32]. In place. */
+int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t key_bits,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIF_B200_QXMATCH_H */

@@ -1,0 +1,531 @@
+// C ABI + host orchestration of the device pipeline (see include/vif_b200_qxmatch.h).
+//
+// Pipeline of one call (cell-binned path):
+//   bbox(cat1), bbox(cat2)            -> 10 scalars D2H, host geometry (xm_geometry.cpp)
+//   per catalog: keys -> radix sort -> cell ranges + gather to cell-ordered SoA
+//   forward ring search (cat1 rows over cat2 cells), reverse ring search (cat2 rows over cat1)
+// There is no CPU fallback anywhere in this file: without a usable device every entry point
+// returns XM_ERR_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "xm_common.cuh"
+
+namespace xm {
+
+int32_t fail_cuda(Error& err, cudaError_t e, const char* what, const char* file, int line) {
+    err.code = XM_ERR_CUDA;
+    snprintf(err.msg, sizeof(err.msg), "CUDA error %d (%s) in %s at %s:%d", (int)e,
+             cudaGetErrorString(e), what, file, line);
+    return err.code;
+}
+
+int32_t fail(Error& err, int32_t code, const char* fmt, ...) {
+    err.code = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err.msg, sizeof(err.msg), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+struct Context {
+    int          device = -1;
+    cudaStream_t stream = nullptr;
+    std::mutex   mu;
+    int          sin_model = 1;
+    unsigned long long* d_small = nullptr;   // 16 u64: two bounding boxes + spare
+    unsigned long long* h_small = nullptr;   // pinned mirror
+    SearchCounters*     d_ctr = nullptr;
+    SearchCounters*     h_ctr = nullptr;     // pinned
+    xm_stats     last;
+    cudaEvent_t  ev[10];
+};
+
+std::mutex g_mu;
+std::map<int, std::unique_ptr<Context>> g_ctx;
+
+int32_t get_context(int32_t device, Context** out, Error& err) {
+    if (device < 0) XM_CUDA_TRY(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) { *out = it->second.get(); return XM_OK; }
+    int count = 0;
+    XM_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device >= count) return fail(err, XM_ERR_CUDA, "CUDA device %d not present (%d visible)", device, count);
+    int prev = 0;
+    XM_CUDA_TRY(cudaGetDevice(&prev));
+    XM_CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<Context> c(new Context);
+    c->device = device;
+    memset(&c->last, 0, sizeof(c->last));
+    XM_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    XM_CUDA_TRY(cudaMalloc(&c->d_small, 16*sizeof(unsigned long long)));
+    XM_CUDA_TRY(cudaMallocHost(&c->h_small, 16*sizeof(unsigned long long)));
+    XM_CUDA_TRY(cudaMalloc(&c->d_ctr, sizeof(SearchCounters)));
+    XM_CUDA_TRY(cudaMallocHost(&c->h_ctr, sizeof(SearchCounters)));
+    for (auto& e : c->ev) XM_CUDA_TRY(cudaEventCreate(&e));
+    // keep freed scratch in the stream-ordered pool: repeated calls then never hit cudaMalloc
+    cudaMemPool_t pool;
+    XM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    XM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    c->sin_model = calibrate_sin_model();
+    XM_CUDA_TRY(cudaSetDevice(prev));
+    *out = c.get();
+    g_ctx[device] = std::move(c);
+    return XM_OK;
+}
+
+// stream-ordered scratch buffer
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t st) {
+        s = st;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, st);
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool armed = false;
+    cudaError_t set(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != dev) { e = cudaSetDevice(dev); armed = (e == cudaSuccess); }
+        return e;
+    }
+    ~DeviceGuard() { if (armed) cudaSetDevice(prev); }
+};
+
+double ord2f(unsigned long long o) {
+    unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+    double v;
+    memcpy(&v, &b, sizeof(v));
+    return v;
+}
+
+struct SortedCat {
+    Scratch x, y, c, perm, key, cell;
+    CatView view{};
+};
+
+// keys -> sort -> cell ranges + gather (one catalog)
+int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
+                    uint32_t ncell, SortedCat& out, cudaStream_t s, Error& err, uint64_t* launches,
+                    cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
+    Scratch tmpk, tmpv, sscr;
+    XM_CUDA_TRY(out.x.alloc((size_t)n*8, s));
+    XM_CUDA_TRY(out.y.alloc((size_t)n*8, s));
+    XM_CUDA_TRY(out.c.alloc((size_t)n*8, s));
+    XM_CUDA_TRY(out.perm.alloc((size_t)n*4, s));
+    XM_CUDA_TRY(out.key.alloc((size_t)n*4, s));
+    XM_CUDA_TRY(out.cell.alloc((size_t)ncell*sizeof(uint2), s));
+    XM_CUDA_TRY(tmpk.alloc((size_t)n*4, s));
+    XM_CUDA_TRY(tmpv.alloc((size_t)n*4, s));
+    XM_CUDA_TRY(sscr.alloc(sort_scratch_bytes(n), s));
+    int32_t rc = launch_keys(ra, dec, n, g, out.key.as<uint32_t>(), out.perm.as<uint32_t>(), s, err, launches);
+    if (rc) return rc;
+    if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (uint64_t)ncell) ++bits;
+    rc = launch_sort_pairs(out.key.as<uint32_t>(), out.perm.as<uint32_t>(), tmpk.as<uint32_t>(),
+                           tmpv.as<uint32_t>(), n, bits, sscr.p, s, err, launches);
+    if (rc) return rc;
+    if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
+    rc = launch_cells_and_gather(out.key.as<uint32_t>(), out.perm.as<uint32_t>(), ra, dec, n, ncell,
+                                 g.linear != 0, out.x.as<double>(), out.y.as<double>(),
+                                 out.c.as<double>(), out.cell.as<uint2>(), s, err, launches);
+    if (rc) return rc;
+    out.view.x = out.x.as<double>(); out.view.y = out.y.as<double>(); out.view.c = out.c.as<double>();
+    out.view.perm = out.perm.as<uint32_t>(); out.view.key = out.key.as<uint32_t>();
+    out.view.cell = out.cell.as<uint2>(); out.view.n = n;
+    return XM_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
+                   const double* ra2, const double* dec2, uint64_t n2, const xm_params& P,
+                   uint64_t* id, double* d, uint64_t* rid, double* rd, Error& err) {
+    const uint64_t nth = P.nth < 1 ? 1 : P.nth;
+    const bool mirror = !P.no_mirror;
+    const bool linear = P.linear != 0;
+    const bool self = P.self != 0;
+    const double dnan = __builtin_nan(""), dinf = __builtin_inf();
+    xm_stats& st = ctx->last;
+    const int sin_model = ctx->sin_model;
+    memset(&st, 0, sizeof(st));
+    st.sin_model = (uint64_t)sin_model;
+    uint64_t launches = 0;
+    int32_t rc;
+
+    if (n1 >= 0xfffffffeull || n2 >= 0xfffffffeull)
+        return fail(err, XM_ERR_INVALID_ARG, "catalogs of 2^32-2 rows or more are not supported");
+    if (nth > 0xffffffffull) return fail(err, XM_ERR_INVALID_ARG, "nth is too large");
+
+    cudaEvent_t* ev = ctx->ev;
+    XM_CUDA_TRY(cudaEventRecord(ev[0], s));
+
+    // qxmatch.hpp:157-167: outputs start as npos / inf and an empty catalog returns them as is
+    if (n1 == 0 || n2 == 0) {
+        if ((rc = launch_fill_outputs(id, d, nth*n1, dinf, s, err, &launches))) return rc;
+        if (mirror && (rc = launch_fill_outputs(rid, rd, n2, dinf, s, err, &launches))) return rc;
+        XM_CUDA_TRY(cudaStreamSynchronize(s));
+        st.launches = launches;
+        return XM_OK;
+    }
+
+    // bounding boxes + finiteness (qxmatch.hpp:146-149, 232-235)
+    const bool same_cat = (ra1 == ra2 && dec1 == dec2 && n1 == n2);
+    if ((rc = launch_bbox(ra1, dec1, n1, ctx->d_small, s, err, &launches))) return rc;
+    if (!same_cat && (rc = launch_bbox(ra2, dec2, n2, ctx->d_small + 5, s, err, &launches))) return rc;
+    XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_small, ctx->d_small, 10*sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, s));
+    XM_CUDA_TRY(cudaEventRecord(ev[1], s));
+    XM_CUDA_TRY(cudaStreamSynchronize(s));
+    if (same_cat) memcpy(ctx->h_small + 5, ctx->h_small, 5*sizeof(unsigned long long));
+    if (ctx->h_small[4])
+        return fail(err, XM_ERR_NONFINITE_1, "first RA and Dec coordinates contain invalid values (infinite or NaN)");
+    if (ctx->h_small[9])
+        return fail(err, XM_ERR_NONFINITE_2, "second RA and Dec coordinates contain invalid values (infinite or NaN)");
+    double bb1[4], bb2[4];
+    for (int k = 0; k < 4; ++k) { bb1[k] = ord2f(ctx->h_small[k]); bb2[k] = ord2f(ctx->h_small[5 + k]); }
+    if (P.has_bbox1) {
+        // the promised box must contain the rows passed
+        if (P.bbox1[0] > bb1[0] || P.bbox1[1] < bb1[1] || P.bbox1[2] > bb1[2] || P.bbox1[3] < bb1[3])
+            return fail(err, XM_ERR_INVALID_ARG, "bbox1 does not contain the catalog-1 rows passed");
+        for (int k = 0; k < 4; ++k) bb1[k] = P.bbox1[k];
+    }
+
+    XM_CUDA_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(SearchCounters), s));
+
+    GridView g;
+    memset(&g, 0, sizeof(g));
+    g.linear = linear ? 1 : 0;
+    g.sin_model = sin_model;
+
+    if (P.brute_force) {
+        // ---- brute force (qxmatch.hpp:490-526) ----
+        Scratch x1, y1, c1, x2, y2, c2;
+        XM_CUDA_TRY(x1.alloc(n1*8, s)); XM_CUDA_TRY(y1.alloc(n1*8, s)); XM_CUDA_TRY(c1.alloc(n1*8, s));
+        if ((rc = launch_prep_unsorted(ra1, dec1, (uint32_t)n1, linear, x1.as<double>(), y1.as<double>(),
+                                       c1.as<double>(), s, err, &launches))) return rc;
+        const double *px2 = x1.as<double>(), *py2 = y1.as<double>(), *pc2 = c1.as<double>();
+        if (!same_cat) {
+            XM_CUDA_TRY(x2.alloc(n2*8, s)); XM_CUDA_TRY(y2.alloc(n2*8, s)); XM_CUDA_TRY(c2.alloc(n2*8, s));
+            if ((rc = launch_prep_unsorted(ra2, dec2, (uint32_t)n2, linear, x2.as<double>(),
+                                           y2.as<double>(), c2.as<double>(), s, err, &launches))) return rc;
+            px2 = x2.as<double>(); py2 = y2.as<double>(); pc2 = c2.as<double>();
+        }
+        XM_CUDA_TRY(cudaEventRecord(ev[5], s));
+        if ((rc = launch_brute_exact(g, x1.as<double>(), y1.as<double>(), c1.as<double>(), (uint32_t)n1,
+                                     px2, py2, pc2, (uint32_t)n2, self, (uint32_t)nth, n1, id, d,
+                                     nullptr, (uint32_t)n1, false, ctx->d_ctr, s, err, &launches))) return rc;
+        XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+        if (mirror) {
+            // reverse match = the same search with the roles swapped: ascending i, strict '<',
+            // i.e. the thread=1 rule (smallest i wins exact ties, qxmatch.hpp:510-513)
+            if ((rc = launch_brute_exact(g, px2, py2, pc2, (uint32_t)n2, x1.as<double>(), y1.as<double>(),
+                                         c1.as<double>(), (uint32_t)n1, self, 1u, n2, rid, rd, nullptr,
+                                         (uint32_t)n2, true, ctx->d_ctr, s, err, &launches))) return rc;
+        }
+        XM_CUDA_TRY(cudaEventRecord(ev[7], s));
+        XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
+        XM_CUDA_TRY(cudaEventRecord(ev[8], s));
+        XM_CUDA_TRY(cudaStreamSynchronize(s));
+        st.ms_bbox = ev_ms(ev[0], ev[1]);
+        st.ms_index = ev_ms(ev[1], ev[5]);
+    } else {
+        // ---- cell-binned path (qxmatch.hpp:230-489) ----
+        xm_grid G;
+        grid_from_bbox(bb1, bb2, n2, nth, linear, &G);
+        st.grid = G;
+        if (G.nra == 0 || G.ndec == 0 || G.nra > 0x7fffffffull || G.ndec > 0x7fffffffull ||
+            G.nra*G.ndec > XM_MAX_CELLS)
+            return fail(err, XM_ERR_GRID_TOO_LARGE,
+                        "bucket grid of %llu x %llu cells (cell size %.3g) is too large; the catalogs "
+                        "span too wide a field for the cell-binned path (use brute_force)",
+                        (unsigned long long)G.nra, (unsigned long long)G.ndec, G.cell_size);
+        const uint32_t ncell = (uint32_t)(G.nra*G.ndec);
+        g.rra0 = G.rra0; g.rdec0 = G.rdec0; g.dra = G.dra; g.ddec = G.ddec; g.cell_size = G.cell_size;
+        g.nra = (uint32_t)G.nra; g.ndec = (uint32_t)G.ndec;
+        g.max_depth = g.nra > g.ndec ? g.nra : g.ndec;
+        const double unit = linear ? 1.0 : XM_D2R;
+        g.ox = G.rra0*unit; g.oy = G.rdec0*unit; g.wx = G.dra*unit; g.wy = G.ddec*unit;
+        // binning rounds (v - origin)/width: edges are uncertain by a few ulp of the largest
+        // coordinate magnitude; 1e-12 relative leaves three orders of magnitude of margin
+        const double mx = fmax(fmax(fabs(G.rra0), fabs(G.rra1)), G.dra);
+        const double my = fmax(fmax(fabs(G.rdec0), fabs(G.rdec1)), G.ddec);
+        g.fzx = 1e-12*mx*unit; g.fzy = 1e-12*my*unit;
+
+        Scratch cmin;
+        XM_CUDA_TRY(cmin.alloc((size_t)g.ndec*8, s));
+        g.cmin_row = cmin.as<double>();
+        if (!linear && (rc = launch_cmin_rows(g, cmin.as<double>(), s, err, &launches))) return rc;
+
+        SortedCat s1, s2;
+        if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, s1, s, err, &launches, ev[2], ev[3]))) return rc;
+        const CatView* v2 = &s1.view;
+        if (!same_cat) {
+            if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, s2, s, err, &launches, nullptr, nullptr))) return rc;
+            v2 = &s2.view;
+        }
+        XM_CUDA_TRY(cudaEventRecord(ev[5], s));
+
+        // qxmatch.hpp:383-387: nth is lowered to n2 after allocation; planes >= n2 keep npos / NaN
+        const uint32_t nth_eff = (uint32_t)(n2 < nth ? n2 : nth);
+        if (nth_eff < nth) {
+            if ((rc = launch_fill_outputs(id, d, nth*n1, linear ? dinf : dnan, s, err, &launches))) return rc;
+        }
+        // `self` with two different arrays is legal in the reference (i == j skipped by index);
+        // the shared-index shortcut (slot equality) only applies when the arrays are the same
+        if (self && !same_cat)
+            return fail(err, XM_ERR_INVALID_ARG, "self=true requires catalog 2 to be catalog 1 (same pointers)");
+        if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, nth_eff, n1, id, d, nullptr,
+                                           (uint32_t)n1, false, ctx->d_ctr, s, err, &launches))) return rc;
+        XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+        if (mirror) {
+            if (!self) {
+                if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd, nullptr,
+                                                   (uint32_t)n2, true, ctx->d_ctr, s, err, &launches))) return rc;
+            } else {
+                // reverse pass skipped (qxmatch.hpp:395): rid = npos, rd = proxy_to_true(inf)
+                if ((rc = launch_fill_outputs(rid, rd, n2, linear ? dinf : dnan, s, err, &launches))) return rc;
+            }
+        }
+        XM_CUDA_TRY(cudaEventRecord(ev[7], s));
+        XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
+        XM_CUDA_TRY(cudaEventRecord(ev[8], s));
+        XM_CUDA_TRY(cudaStreamSynchronize(s));
+        st.ms_bbox = ev_ms(ev[0], ev[1]);
+        st.ms_keys = ev_ms(ev[1], ev[2]);
+        st.ms_sort = ev_ms(ev[2], ev[3]);
+        st.ms_index = ev_ms(ev[1], ev[5]);
+    }
+    st.ms_forward = ev_ms(ev[5], ev[6]);
+    st.ms_reverse = ev_ms(ev[6], ev[7]);
+    st.ms_total = ev_ms(ev[0], ev[8]);
+    st.launches = launches;
+    st.evals_fwd = ctx->h_ctr->evals_fwd; st.evals_rev = ctx->h_ctr->evals_rev;
+    st.rows_ambiguous = ctx->h_ctr->ambiguous;
+    st.rows_refined_fwd = ctx->h_ctr->refine_fwd; st.rows_refined_rev = ctx->h_ctr->refine_rev;
+    if (P.verbose) {
+        printf("[vif_b200] qxmatch n1=%llu n2=%llu nth=%llu %s: %.3f ms on device (index %.3f, forward %.3f, "
+               "reverse %.3f), %llu kernel launches\n", (unsigned long long)n1, (unsigned long long)n2,
+               (unsigned long long)nth, P.brute_force ? "brute" : "binned", st.ms_total, st.ms_index,
+               st.ms_forward, st.ms_reverse, (unsigned long long)launches);
+        fflush(stdout);
+    }
+    return XM_OK;
+}
+
+void copy_err(const Error& err, char* errbuf, uint64_t errcap) {
+    if (errbuf && errcap) {
+        strncpy(errbuf, err.msg, errcap - 1);
+        errbuf[errcap - 1] = 0;
+    }
+}
+
+int32_t check_args(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,
+                   const double* dec2, uint64_t n2, const xm_params* p, uint64_t* id, double* d,
+                   uint64_t* rid, double* rd, Error& err) {
+    if (!p) return fail(err, XM_ERR_INVALID_ARG, "params is NULL");
+    if ((n1 && (!ra1 || !dec1)) || (n2 && (!ra2 || !dec2)))
+        return fail(err, XM_ERR_INVALID_ARG, "NULL coordinate pointer");
+    if (n1 && (!id || !d)) return fail(err, XM_ERR_INVALID_ARG, "NULL id/d output pointer");
+    if (!p->no_mirror && n2 && (!rid || !rd))
+        return fail(err, XM_ERR_INVALID_ARG, "NULL rid/rd output pointer while no_mirror is false");
+    return XM_OK;
+}
+
+}  // namespace
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" {
+
+const char* xm_version(void) { return "vif_b200_qxmatch 0.1 (sm_100a)"; }
+
+int32_t xm_init(int32_t device, char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* c = nullptr;
+    int32_t rc = get_context(device, &c, err);
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+void xm_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_ctx) {
+        Context* c = kv.second.get();
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        for (auto& e : c->ev) cudaEventDestroy(e);
+        cudaFree(c->d_small); cudaFreeHost(c->h_small);
+        cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr);
+        cudaStreamDestroy(c->stream);
+    }
+    g_ctx.clear();
+}
+
+int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,
+                       const double* dec2, uint64_t n2, const xm_params* params, uint64_t* id,
+                       double* d, uint64_t* rid, double* rd, void* stream, char* errbuf,
+                       uint64_t errcap) {
+    Error err;
+    int32_t rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
+    Context* ctx = nullptr;
+    if (!rc) rc = get_context(params->device, &ctx, err);
+    if (!rc) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        DeviceGuard dg;
+        cudaError_t e = dg.set(ctx->device);
+        if (e != cudaSuccess) rc = fail_cuda(err, e, "cudaSetDevice", __FILE__, __LINE__);
+        else {
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            rc = run_device(ctx, s, ra1, dec1, n1, ra2, dec2, n2, *params, id, d, rid, rd, err);
+            if (rc == XM_ERR_CUDA) { cudaStreamSynchronize(s); cudaGetLastError(); }
+        }
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,
+                       const double* dec2, uint64_t n2, const xm_params* params, uint64_t* id,
+                       double* d, uint64_t* rid, double* rd, char* errbuf, uint64_t errcap) {
+    Error err;
+    int32_t rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
+    Context* ctx = nullptr;
+    if (!rc) rc = get_context(params->device, &ctx, err);
+    if (rc) { copy_err(err, errbuf, errcap); return rc; }
+
+    auto body = [&]() -> int32_t {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        DeviceGuard dg;
+        XM_CUDA_TRY(dg.set(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const uint64_t nth = params->nth < 1 ? 1 : params->nth;
+        const bool mirror = !params->no_mirror;
+        const bool same_cat = (ra1 == ra2 && dec1 == dec2 && n1 == n2);
+        Scratch dra1, ddec1, dra2, ddec2, did, dd, drid, drd;
+        XM_CUDA_TRY(dra1.alloc(n1*8, s)); XM_CUDA_TRY(ddec1.alloc(n1*8, s));
+        XM_CUDA_TRY(cudaMemcpyAsync(dra1.p, ra1, n1*8, cudaMemcpyHostToDevice, s));
+        XM_CUDA_TRY(cudaMemcpyAsync(ddec1.p, dec1, n1*8, cudaMemcpyHostToDevice, s));
+        const double *pra2 = dra1.as<double>(), *pdec2 = ddec1.as<double>();
+        if (!same_cat) {
+            XM_CUDA_TRY(dra2.alloc(n2*8, s)); XM_CUDA_TRY(ddec2.alloc(n2*8, s));
+            XM_CUDA_TRY(cudaMemcpyAsync(dra2.p, ra2, n2*8, cudaMemcpyHostToDevice, s));
+            XM_CUDA_TRY(cudaMemcpyAsync(ddec2.p, dec2, n2*8, cudaMemcpyHostToDevice, s));
+            pra2 = dra2.as<double>(); pdec2 = ddec2.as<double>();
+        }
+        XM_CUDA_TRY(did.alloc(nth*n1*8, s)); XM_CUDA_TRY(dd.alloc(nth*n1*8, s));
+        if (mirror) { XM_CUDA_TRY(drid.alloc(n2*8, s)); XM_CUDA_TRY(drd.alloc(n2*8, s)); }
+        int32_t r = run_device(ctx, s, dra1.as<double>(), ddec1.as<double>(), n1, pra2, pdec2, n2, *params,
+                               did.as<uint64_t>(), dd.as<double>(), drid.as<uint64_t>(), drd.as<double>(), err);
+        if (r) return r;
+        XM_CUDA_TRY(cudaMemcpyAsync(id, did.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
+        XM_CUDA_TRY(cudaMemcpyAsync(d, dd.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
+        if (mirror) {
+            XM_CUDA_TRY(cudaMemcpyAsync(rid, drid.p, n2*8, cudaMemcpyDeviceToHost, s));
+            XM_CUDA_TRY(cudaMemcpyAsync(rd, drd.p, n2*8, cudaMemcpyDeviceToHost, s));
+        }
+        XM_CUDA_TRY(cudaStreamSynchronize(s));
+        return XM_OK;
+    };
+    rc = body();
+    if (rc == XM_ERR_CUDA) { cudaDeviceSynchronize(); cudaGetLastError(); }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+int32_t xm_grid_from_bbox(const double* bbox1, const double* bbox2, uint64_t n2, uint64_t nth,
+                          int32_t linear, xm_grid* out) {
+    if (!bbox1 || !bbox2 || !out) return XM_ERR_INVALID_ARG;
+    grid_from_bbox(bbox1, bbox2, n2, nth < 1 ? 1 : nth, linear != 0, out);
+    return XM_OK;
+}
+
+int32_t xm_bbox_dev(const double* ra, const double* dec, uint64_t n, int32_t device, void* stream,
+                    double* out, uint64_t* nonfinite, char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = (!ra || !dec || !out || n == 0) ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            uint64_t launches = 0;
+            int32_t r = launch_bbox(ra, dec, n, ctx->d_small, s, err, &launches);
+            if (r) return r;
+            XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_small, ctx->d_small, 5*sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToHost, s));
+            XM_CUDA_TRY(cudaStreamSynchronize(s));
+            for (int k = 0; k < 4; ++k) out[k] = ord2f(ctx->h_small[k]);
+            if (nonfinite) *nonfinite = ctx->h_small[4];
+            return XM_OK;
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+int32_t xm_last_stats(int32_t device, xm_stats* out) {
+    if (!out) return XM_ERR_INVALID_ARG;
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = get_context(device, &ctx, err);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->last;
+    return XM_OK;
+}
+
+int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t key_bits,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = (!keys || !vals || n >= 0xfffffffeull) ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            Scratch tk, tv, sc;
+            XM_CUDA_TRY(tk.alloc(n*4, s)); XM_CUDA_TRY(tv.alloc(n*4, s));
+            XM_CUDA_TRY(sc.alloc(sort_scratch_bytes(n), s));
+            uint64_t launches = 0;
+            int32_t r = launch_sort_pairs(keys, vals, tk.as<uint32_t>(), tv.as<uint32_t>(), (uint32_t)n,
+                                          key_bits, sc.p, s, err, &launches);
+            if (r) return r;
+            XM_CUDA_TRY(cudaStreamSynchronize(s));
+            return XM_OK;
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+}  // extern "C"

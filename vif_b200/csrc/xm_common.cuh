@@ -1,0 +1,104 @@
+// Shared declarations of the qxmatch device pipeline (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/vif_b200_qxmatch.h"
+
+namespace xm {
+
+// ---- constants (math/base.hpp:20, qxmatch.hpp:174) -----------------------------------------
+// dpi is written with 18 digits in the reference and rounds to the double nearest pi.
+#define XM_DPI 3.14159265358979323
+#define XM_D2R (XM_DPI/180.0)
+
+// ---- device-side views ---------------------------------------------------------------------
+// One catalog sorted by cell key. x,y are radians (raw units when linear), c = cos(y).
+struct CatView {
+    const double*   x;
+    const double*   y;
+    const double*   c;
+    const uint32_t* perm;   // sorted position -> original row
+    const uint32_t* key;    // sorted cell keys (ix*ndec + iy)
+    const uint2*    cell;   // per cell: [begin, end) in sorted order (0,0 when empty)
+    uint32_t        n;
+};
+
+struct GridView {
+    double   rra0, rdec0;     // padded origin [deg, or raw units when linear] -- binning units
+    double   dra, ddec;       // cell widths in binning units
+    double   cell_size;       // [arcsec, or raw units when linear]
+    double   ox, oy, wx, wy;  // the same grid in search units (radians, or raw units when linear)
+    double   fzx, fzy;        // slack on cell edges in search units: covers the rounding of the
+                              // binning expression so that cell lower bounds stay rigorous
+    const double* cmin_row;   // per cell row: lower bound of cos(dec) over the row (spherical)
+    uint32_t nra, ndec;
+    uint32_t max_depth;       // max(nra, ndec): depth_cache::size(), qxmatch.hpp:85-87
+    int32_t  linear;
+    int32_t  sin_model;       // 1: glibc __sin_fma Taylor branch, 2: non-FMA build of the same
+};
+
+struct SearchCounters {       // device counters, zeroed per call
+    unsigned long long evals_fwd, evals_rev, ambiguous, refine_fwd, refine_rev;
+};
+
+// ---- error plumbing ------------------------------------------------------------------------
+struct Error {
+    int32_t code = XM_OK;
+    char    msg[512] = {0};
+};
+
+#define XM_CUDA_TRY(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            return xm::fail_cuda(err, _e, #expr, __FILE__, __LINE__);                            \
+        }                                                                                        \
+    } while (0)
+
+int32_t fail_cuda(Error& err, cudaError_t e, const char* what, const char* file, int line);
+int32_t fail(Error& err, int32_t code, const char* fmt, ...);
+
+// ---- host geometry (xm_geometry.cpp) ------------------------------------------------------
+void grid_from_bbox(const double* bb1, const double* bb2, uint64_t n2, uint64_t nth, bool linear,
+                    xm_grid* g);
+int  calibrate_sin_model();   // probes the host libm: 1 = FMA Taylor model, 2 = non-FMA
+
+// ---- launchers -----------------------------------------------------------------------------
+// xm_index.cu
+int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
+                    cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridView& g,
+                    uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
+                                const double* dec, uint32_t n, uint32_t ncell, bool linear,
+                                double* x, double* y, double* c, uint2* cell, cudaStream_t s,
+                                Error& err, uint64_t* launches);
+// xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
+// by sort_scratch_bytes(n)
+size_t  sort_scratch_bytes(uint64_t n);
+int32_t launch_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* tmp_keys, uint32_t* tmp_vals,
+                          uint32_t n, int key_bits, void* scratch, cudaStream_t s, Error& err,
+                          uint64_t* launches);
+// xm_search_exact.cu: reference-order arithmetic (compiled with -fmad=false)
+int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const CatView& cand,
+                                 bool self, uint32_t nth_eff, uint64_t plane_stride,
+                                 uint64_t* id_out, double* d_out, const uint32_t* rows,
+                                 uint32_t nrows, bool reverse, SearchCounters* ctr,
+                                 cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_cmin_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err,
+                         uint64_t* launches);
+int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1, const double* c1,
+                           uint32_t n1, const double* x2, const double* y2, const double* c2,
+                           uint32_t n2, bool self, uint32_t nth_eff, uint64_t plane_stride,
+                           uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows,
+                           bool reverse, SearchCounters* ctr, cudaStream_t s, Error& err,
+                           uint64_t* launches);
+int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
+                             double* x, double* y, double* c, cudaStream_t s, Error& err,
+                             uint64_t* launches);
+int32_t launch_fill_outputs(uint64_t* id, double* d, uint64_t n, double dval, cudaStream_t s,
+                            Error& err, uint64_t* launches);
+
+}  // namespace xm

@@ -1,0 +1,151 @@
+// Cell index construction: bounding box + finiteness, cell keys, CSR cell ranges and the
+// gather of each catalog into cell order (SoA: x = ra [rad], y = dec [rad], c = cos(dec)).
+//
+// Replaces the reference's eight min/max passes (qxmatch.hpp:232-235), the finiteness checks
+// (:146-149), the unit conversion (:170-181) and the vector-of-vectors bucket fill (:270-288).
+// All of it is HBM-bound streaming work: coalesced loads, one pass per array.
+#include "xm_common.cuh"
+
+namespace xm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// order-preserving map double -> u64 so that min/max can use integer atomics
+__device__ __forceinline__ unsigned long long f2ord(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) {
+    return a < b ? a : b;
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
+    return a > b ? a : b;
+}
+
+// out5 = {ord(min ra), ord(max ra), ord(min dec), ord(max dec), nonfinite count}
+__global__ void __launch_bounds__(kThreads)
+bbox_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint64_t n,
+            unsigned long long* __restrict__ out5) {
+    unsigned long long lo_r = ~0ull, hi_r = 0ull, lo_d = ~0ull, hi_d = 0ull, bad = 0;
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double r = __ldg(ra + i), d = __ldg(dec + i);
+        if (isfinite(r) && isfinite(d)) {
+            const unsigned long long a = f2ord(r), b = f2ord(d);
+            lo_r = umin64(lo_r, a); hi_r = umax64(hi_r, a);
+            lo_d = umin64(lo_d, b); hi_d = umax64(hi_d, b);
+        } else {
+            ++bad;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_r = umin64(lo_r, __shfl_xor_sync(0xffffffffu, lo_r, o));
+        hi_r = umax64(hi_r, __shfl_xor_sync(0xffffffffu, hi_r, o));
+        lo_d = umin64(lo_d, __shfl_xor_sync(0xffffffffu, lo_d, o));
+        hi_d = umax64(hi_d, __shfl_xor_sync(0xffffffffu, hi_d, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __shared__ unsigned long long sm[5][kThreads/32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm[0][w] = lo_r; sm[1][w] = hi_r; sm[2][w] = lo_d; sm[3][w] = hi_d; sm[4][w] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads/32; ++k) {
+            lo_r = umin64(lo_r, sm[0][k]); hi_r = umax64(hi_r, sm[1][k]);
+            lo_d = umin64(lo_d, sm[2][k]); hi_d = umax64(hi_d, sm[3][k]);
+            bad += sm[4][k];
+        }
+        atomicMin(out5 + 0, lo_r); atomicMax(out5 + 1, hi_r);
+        atomicMin(out5 + 2, lo_d); atomicMax(out5 + 3, hi_d);
+        if (bad) atomicAdd(out5 + 4, bad);
+    }
+}
+
+__global__ void bbox_init_kernel(unsigned long long* out5) {
+    out5[0] = ~0ull; out5[1] = 0ull; out5[2] = ~0ull; out5[3] = 0ull; out5[4] = 0ull;
+}
+
+// qxmatch.hpp:278-279: idx = floor((ra - rra0)/dra), idy = floor((dec - rdec0)/ddec) on the raw
+// inputs; IEEE subtract, divide and floor only, so the keys equal the reference's buckets.
+__global__ void __launch_bounds__(kThreads)
+keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, double rra0,
+            double rdec0, double dra, double ddec, uint32_t nra, uint32_t ndec,
+            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double fx = floor(__ddiv_rn(__dsub_rn(__ldg(ra + i), rra0), dra));
+    const double fy = floor(__ddiv_rn(__dsub_rn(__ldg(dec + i), rdec0), ddec));
+    // with has_bbox1 a caller could hand us rows outside the box it promised: clamp instead of
+    // writing out of bounds (rows inside the box are unaffected)
+    uint32_t ix = fx < 0 ? 0u : (fx >= (double)nra ? nra - 1 : (uint32_t)fx);
+    uint32_t iy = fy < 0 ? 0u : (fy >= (double)ndec ? ndec - 1 : (uint32_t)fy);
+    keys[i] = ix*ndec + iy;
+    vals[i] = i;
+}
+
+// One pass over the sorted keys: cell ranges by boundary detection (no scan needed; the cell
+// table was zeroed, so empty cells read as [0,0)) fused with the gather into cell order and the
+// unit conversion (:174-180).
+__global__ void __launch_bounds__(kThreads)
+cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
+                    const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
+                    int linear, double* __restrict__ x, double* __restrict__ y,
+                    double* __restrict__ c, uint2* __restrict__ cell) {
+    const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t k = skeys[p];
+    const uint32_t kprev = p > 0 ? skeys[p - 1] : 0xffffffffu;
+    const uint32_t knext = p + 1 < n ? skeys[p + 1] : 0xffffffffu;
+    if (p == 0 || k != kprev) cell[k].x = p;
+    if (p + 1 == n || k != knext) cell[k].y = p + 1;
+    const uint32_t i = perm[p];
+    const double r = __ldg(ra + i), d = __ldg(dec + i);
+    if (linear) {
+        x[p] = r; y[p] = d; c[p] = 1.0;
+    } else {
+        const double yr = __dmul_rn(d, XM_D2R);
+        x[p] = __dmul_rn(r, XM_D2R);
+        y[p] = yr;
+        c[p] = cos(yr);
+    }
+}
+
+}  // namespace
+
+int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
+                    cudaStream_t s, Error& err, uint64_t* launches) {
+    bbox_init_kernel<<<1, 1, 0, s>>>(out5);
+    uint64_t blocks = (n + kThreads*8 - 1)/(kThreads*8);
+    if (blocks > 148*16) blocks = 148*16;
+    if (blocks < 1) blocks = 1;
+    bbox_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(ra, dec, n, out5);
+    *launches += 2;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridView& g,
+                    uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches) {
+    keys_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(ra, dec, n, g.rra0, g.rdec0, g.dra,
+                                                                g.ddec, g.nra, g.ndec, keys, vals);
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
+                                const double* dec, uint32_t n, uint32_t ncell, bool linear,
+                                double* x, double* y, double* c, uint2* cell, cudaStream_t s,
+                                Error& err, uint64_t* launches) {
+    XM_CUDA_TRY(cudaMemsetAsync(cell, 0, (size_t)ncell*sizeof(uint2), s));
+    cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
+                                                                        linear ? 1 : 0, x, y, c, cell);
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+}  // namespace xm

@@ -1,0 +1,87 @@
+// Reference-order FP64 arithmetic for the parity-critical expressions.
+//
+// Every operation here is spelled with __d*_rn / __fma_rn intrinsics so that nvcc can neither
+// contract nor reassociate, whatever -fmad says: x86-64 gcc without -mfma (the reference's flags,
+// CMakeLists.txt:54-58) evaluates the same expressions as separately rounded IEEE operations.
+// IEEE + - * / sqrt floor are then bit-identical host/device; only sin/cos/asin can differ.
+//
+// sin(): glibc 2.39's double sin takes, for 2^-26 <= |x| < 0.126, a degree-11 odd Taylor branch
+// (sysdeps/ieee754/dbl-64/s_sin.c, TAYLOR_SIN with dx = 0). That branch is plain IEEE arithmetic,
+// so it is restated here and is bit-identical to the host libm on the whole range the cell-binned
+// search ever feeds it (half-differences of coordinates a few cells apart). On x86-64 hosts with
+// FMA, glibc dispatches to the -mfma build of the same source, in which the Horner steps contract;
+// xm_init() probes the host libm on a dozen discriminating inputs and selects the matching model
+// (GridView::sin_model). Outside that range the CUDA libm sin (<= 2 ulp) is used.
+#pragma once
+#include "xm_common.cuh"
+
+namespace xm {
+
+__device__ __forceinline__ double sin_taylor_glibc(double x, int model) {
+    const double s1 = -0x1.5555555555555p-3, s2 = 0x1.1111111110ECEp-7, s3 = -0x1.A01A019DB08B8p-13,
+                 s4 = 0x1.71DE27B9A7ED9p-19, s5 = -0x1.ADDFFC2FCDF59p-26;
+    const double xx = __dmul_rn(x, x);
+    double p;
+    if (model == 1) {
+        p = __fma_rn(__fma_rn(__fma_rn(__fma_rn(s5, xx, s4), xx, s3), xx, s2), xx, s1);
+    } else {
+        p = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(
+                __dmul_rn(s5, xx), s4), xx), s3), xx), s2), xx), s1);
+    }
+    const double t = __dmul_rn(__dmul_rn(p, x), xx);
+    return __dadd_rn(x, t);
+}
+
+__device__ __forceinline__ double sin_ref(double x, int model) {
+    const double ax = fabs(x);
+    if (ax < 0.126) {
+        if (ax < 0x1p-26) return x;
+        return sin_taylor_glibc(x, model);
+    }
+    return sin(x);
+}
+
+// qxmatch.hpp:200-202: sde*sde + sra*sra*dcdec2*dcdec1, left to right.
+__device__ __forceinline__ double proxy_sph(double x1, double y1, double c1, double x2, double y2,
+                                            double c2, int model) {
+    const double sra = sin_ref(__dmul_rn(0.5, __dsub_rn(x2, x1)), model);
+    const double sde = sin_ref(__dmul_rn(0.5, __dsub_rn(y2, y1)), model);
+    return __dadd_rn(__dmul_rn(sde, sde),
+                     __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), c2), c1));
+}
+
+// qxmatch.hpp:198: sqr(ra2 - ra1) + sqr(dec2 - dec1) on the raw inputs.
+__device__ __forceinline__ double proxy_lin(double x1, double y1, double x2, double y2) {
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// qxmatch.hpp:206-214
+__device__ __forceinline__ double true_to_proxy(double dist, bool linear, int model) {
+    if (linear) return __dmul_rn(dist, dist);
+    const double k = __dmul_rn(__dmul_rn(3600.0, __ddiv_rn(180.0, XM_DPI)), 2.0);
+    const double s = sin_ref(__ddiv_rn(dist, k), model);
+    return __dmul_rn(s, s);
+}
+
+// qxmatch.hpp:215-222
+__device__ __forceinline__ double proxy_to_true(double p, bool linear) {
+    if (linear) return __dsqrt_rn(p);
+    const double k = __dmul_rn(__dmul_rn(3600.0, __ddiv_rn(180.0, XM_DPI)), 2.0);
+    return __dmul_rn(k, asin(__dsqrt_rn(p)));
+}
+
+// astro.hpp:33-39 (angdist, degrees -> arcsec) with the first point already converted:
+// x1r = d2r*ra1, y1r = d2r*dec1, c1 = cos(y1r).
+__device__ __forceinline__ double angdist_pre(double x1r, double y1r, double c1, double tra2,
+                                              double tdec2, int model) {
+    const double d2r = XM_D2R;
+    const double ra2 = __dmul_rn(d2r, tra2), dec2 = __dmul_rn(d2r, tdec2);
+    const double sra = sin_ref(__dmul_rn(0.5, __dsub_rn(ra2, x1r)), model);
+    const double sde = sin_ref(__dmul_rn(0.5, __dsub_rn(dec2, y1r)), model);
+    const double h = __dadd_rn(__dmul_rn(sde, sde),
+                               __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cos(dec2)), c1));
+    return __ddiv_rn(__dmul_rn(__dmul_rn(3600.0, 2.0), asin(__dsqrt_rn(h))), d2r);
+}
+
+}  // namespace xm
