@@ -146,6 +146,12 @@ int32_t xm_last_stats(int32_t device, xm_stats* out);
 int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t key_bits,
                           int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
+/* Host-only: entry list of ring `k` of the reference's depth_cache (qxmatch.hpp:44-128) for an
+ * (nx, ny) grid, in visiting order, as the kernels enumerate it (closed form, no table). Writes up
+ * to `cap` (bx, by) pairs, returns the entry count. dedupe != 0 drops the repeated axis cells. */
+uint64_t xm_ring_entries(uint32_t k, uint32_t nx, uint32_t ny, int32_t dedupe,
+                         int32_t* bx, int32_t* by, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

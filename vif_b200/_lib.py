@@ -42,7 +42,7 @@ class XmStats(C.Structure):
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
 SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_qxmatch_f64", "xm_qxmatch_dev",
-           "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev"]
+           "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries"]
 
 _lib = None
 
@@ -76,5 +76,8 @@ def load():
     lib.xm_last_stats.argtypes = [i32, C.POINTER(XmStats)]
     lib.xm_sort_pairs_dev.restype = i32
     lib.xm_sort_pairs_dev.argtypes = [vp, vp, u64, i32, i32, vp, C.c_char_p, u64]
+    lib.xm_ring_entries.restype = u64
+    lib.xm_ring_entries.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, i32, C.POINTER(i32),
+                                    C.POINTER(i32), u64]
     _lib = lib
     return lib

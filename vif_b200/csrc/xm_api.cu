@@ -14,6 +14,7 @@
 #include <mutex>
 
 #include "xm_common.cuh"
+#include "xm_ring.cuh"
 
 namespace xm {
 
@@ -526,6 +527,17 @@ int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t ke
     }
     if (rc) copy_err(err, errbuf, errcap);
     return rc;
+}
+
+uint64_t xm_ring_entries(uint32_t k, uint32_t nx, uint32_t ny, int32_t dedupe, int32_t* bx,
+                         int32_t* by, uint64_t cap) {
+    uint64_t n = 0;
+    if (nx == 0 || ny == 0) return 0;
+    for_each_ring_entry(k, nx, ny, dedupe != 0, [&](int x, int y) {
+        if (n < cap && bx && by) { bx[n] = x; by[n] = y; }
+        ++n;
+    });
+    return n;
 }
 
 }  // extern "C"

@@ -1,0 +1,99 @@
+"""Row-sharded multi-GPU qxmatch: one process per GPU, `torch.distributed` (NCCL over NVLink) for
+the plumbing. Mirrors how the reference splits work between its std::threads -- contiguous chunks
+of catalog-1 rows per worker (qxmatch.hpp:422-459) -- with one exchange step for the reverse match.
+
+  1. catalog 2 is replicated: `dist.broadcast` from `src` (NCCL broadcast over NVSwitch);
+  2. the bounding box of catalog 1 is made global with two 2-element all-reduces (min / max), so
+     every rank bins with the grid of qxmatch.hpp:232-267 computed from the WHOLE catalogs;
+  3. every rank runs the single-GPU pipeline on its row shard against the full catalog 2
+     (forward results never leave the rank: rows are independent);
+  4. reverse match: all-reduce(min) on `rd`, then all-reduce(min) on `rid` masked to the ranks
+     whose local distance equals the global minimum => nearest catalog-1 row over all shards, the
+     smallest row index on exact ties (the reference's thread=1 rule, qxmatch.hpp:510-513).
+
+No collective touches the forward path. `compute` and `bbox` are injectable so that the sharding
+and merge logic is testable on CPU with the gloo backend (tests/test_distributed_gloo.py); the
+defaults are the CUDA library and there is no CPU implementation in this module.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous row block [begin, end) of `rank` (floor split, remainder to the last ranks)."""
+    return (n * rank) // world_size, (n * (rank + 1)) // world_size
+
+
+def _cuda_bbox(ra, dec):
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    out = (C.c_double * 4)()
+    bad = C.c_uint64()
+    err = C.create_string_buffer(512)
+    import torch
+    torch.cuda.current_stream(ra.device).synchronize()
+    rc = lib.xm_bbox_dev(ra.data_ptr(), dec.data_ptr(), ra.numel(), ra.device.index or 0, None, out,
+                         C.byref(bad), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return [out[0], out[1], out[2], out[3]]
+
+
+def _cuda_compute(ra1, dec1, ra2, dec2, params):
+    from .qxmatch import qxmatch
+    return qxmatch(ra1, dec1, ra2, dec2, params=params)
+
+
+def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=None, src=0,
+                    broadcast_cat2=True, compute=None, bbox=None):
+    """Runs one rank's part of a row-sharded qxmatch.
+
+    ra1_local/dec1_local: this rank's rows [row_offset, row_offset + len) of catalog 1.
+    ra2/dec2: full-size catalog-2 tensors (contents only need to be valid on `src` when
+    broadcast_cat2). Returns (id_local, d_local, rid, rd): forward results for the local rows,
+    reverse results replicated on every rank with GLOBAL catalog-1 row ids. Ids are int64 bit
+    patterns (NPOS == -1) as in the single-GPU device path.
+    """
+    import torch
+    import torch.distributed as dist
+    from .qxmatch import QxmatchParams
+
+    compute = compute or _cuda_compute
+    bbox = bbox or _cuda_bbox
+    world = dist.get_world_size(group)
+    if params.self:
+        raise ValueError("self-match shards catalog 1 against itself: pass the full catalog as "
+                         "catalog 2 and self=False with an explicit id offset instead")
+    if broadcast_cat2 and world > 1:
+        dist.broadcast(ra2, src=src, group=group)
+        dist.broadcast(dec2, src=src, group=group)
+
+    # global bounding box of catalog 1 (qxmatch.hpp:232-238)
+    bb = bbox(ra1_local, dec1_local)
+    lo = torch.tensor([bb[0], bb[2]], dtype=torch.float64, device=ra1_local.device)
+    hi = torch.tensor([bb[1], bb[3]], dtype=torch.float64, device=ra1_local.device)
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = lo.tolist(), hi.tolist()
+    p = QxmatchParams(**{**params.__dict__, "bbox1": (lo[0], hi[0], lo[1], hi[1])})
+
+    res = compute(ra1_local, dec1_local, ra2, dec2, p)
+    ident, d, rid, rd = res.id, res.d, res.rid, res.rd
+    if p.no_mirror:
+        return ident, d, rid, rd
+
+    big = torch.iinfo(torch.int64).max
+    rid = torch.as_tensor(rid).view(torch.int64) if not isinstance(rid, torch.Tensor) else rid
+    rd = torch.as_tensor(rd) if not isinstance(rd, torch.Tensor) else rd
+    rid = torch.where(rid < 0, torch.full_like(rid, big), rid + int(row_offset))
+    rd_key = torch.where(torch.isnan(rd), torch.full_like(rd, float("inf")), rd)
+    if world > 1:
+        best = rd_key.clone()
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+        rid = torch.where(rd_key == best, rid, torch.full_like(rid, big))
+        dist.all_reduce(rid, op=dist.ReduceOp.MIN, group=group)
+        # distances of unmatched slots stay NaN (spherical) / inf (linear) as in the reference
+        rd = torch.where(rid == big, rd, best)
+    rid = torch.where(rid == big, torch.full_like(rid, -1), rid)
+    return ident, d, rid, rd

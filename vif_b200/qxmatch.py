@@ -94,8 +94,10 @@ def last_stats(device=-1):
     return st.as_dict()
 
 
-def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, **kw):
-    """See module docstring. `params` may be a QxmatchParams; keywords override its fields."""
+def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, out=None, **kw):
+    """See module docstring. `params` may be a QxmatchParams; keywords override its fields.
+    `out` (host path only): dict of preallocated numpy arrays id/d/rid/rd to receive the results,
+    e.g. views of pinned memory so that the D2H copies run at full PCIe rate."""
     p = QxmatchParams(**{**(params.__dict__ if params is not None else {}), **kw})
     if ra2 is None and dec2 is None:
         # qxmatch.hpp:629-634: one catalog -> self match against itself
@@ -106,7 +108,7 @@ def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, **kw):
     lib = _lib.load()
     if _is_torch_cuda(ra1):
         return _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p)
-    return _qxmatch_host(lib, ra1, dec1, ra2, dec2, p)
+    return _qxmatch_host(lib, ra1, dec1, ra2, dec2, p, out)
 
 
 def _check_dims(s1, s2, which):
@@ -116,7 +118,7 @@ def _check_dims(s1, s2, which):
                            "%s RA and Dec dimensions do not match (%s vs %s)" % (which, list(s1), list(s2)))
 
 
-def _qxmatch_host(lib, ra1, dec1, ra2, dec2, p):
+def _qxmatch_host(lib, ra1, dec1, ra2, dec2, p, out=None):
     same = ra2 is ra1 and dec2 is dec1
     a1 = np.ascontiguousarray(ra1, dtype=np.float64)
     b1 = np.ascontiguousarray(dec1, dtype=np.float64)
@@ -130,10 +132,18 @@ def _qxmatch_host(lib, ra1, dec1, ra2, dec2, p):
     a1, b1, a2, b2 = a1.reshape(-1), b1.reshape(-1), a2.reshape(-1), b2.reshape(-1)
     n1, n2 = a1.size, a2.size
     nth = max(int(p.nth), 1)
-    ident = np.empty((nth, n1), dtype=np.uint64)
-    d = np.empty((nth, n1), dtype=np.float64)
-    rid = np.empty(0 if p.no_mirror else n2, dtype=np.uint64)
-    rd = np.empty(0 if p.no_mirror else n2, dtype=np.float64)
+    nrev = 0 if p.no_mirror else n2
+    if out is not None:
+        ident, d, rid, rd = out["id"], out["d"], out["rid"], out["rd"]
+        for arr, shape, dt in ((ident, (nth, n1), np.uint64), (d, (nth, n1), np.float64),
+                               (rid, (nrev,), np.uint64), (rd, (nrev,), np.float64)):
+            if arr.shape != shape or arr.dtype != dt or not arr.flags.c_contiguous:
+                raise TypeError("out[...] arrays must be C-contiguous with the result shapes/dtypes")
+    else:
+        ident = np.empty((nth, n1), dtype=np.uint64)
+        d = np.empty((nth, n1), dtype=np.float64)
+        rid = np.empty(nrev, dtype=np.uint64)
+        rd = np.empty(nrev, dtype=np.float64)
     cp = p.to_c()
     err = C.create_string_buffer(1024)
     rc = lib.xm_qxmatch_f64(a1.ctypes.data, b1.ctypes.data, n1, a2.ctypes.data, b2.ctypes.data, n2,
