@@ -92,6 +92,7 @@ typedef struct xm_stats {
     uint64_t rows_ambiguous;           /* rows whose decisive proxies differ by < 8 ulp            */
     uint64_t evals_fwd, evals_rev;     /* distance evaluations (filter + exact)                    */
     uint64_t sin_model;                /* 1 = glibc FMA Taylor model, 2 = non-FMA model            */
+    double   ms_host;                  /* host wall clock of the whole call (incl. copies)         */
 } xm_stats;
 
 /* Library / ABI version string, e.g. "vif_b200_qxmatch 0.1 (sm_100a)". Never fails. */

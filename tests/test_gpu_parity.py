@@ -95,8 +95,11 @@ def test_errors_nonfinite_and_grid():
     with pytest.raises(QxmatchError, match="second RA and Dec coordinates contain invalid values"):
         qxmatch(b, b, a, np.array([0.1, np.inf, 0.3]))
     ra, dec = G.fullsky(1, 1000)
+    ra2, dec2 = G.fullsky(2, 1000)
+    ra2[:4] = [0.0, 0.0, 360.0, 360.0]           # bounding box = the whole sphere: hull area 0
+    dec2[:4] = [-90.0, 90.0, -90.0, 90.0]
     with pytest.raises(QxmatchError) as e:       # 1-arcsec cells over the whole sky
-        qxmatch(ra, dec, *G.fullsky(2, 1000))
+        qxmatch(ra, dec, ra2, dec2)
     assert e.value.code == _lib.XM_ERR_GRID_TOO_LARGE
 
 

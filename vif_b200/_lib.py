@@ -32,7 +32,7 @@ class XmStats(C.Structure):
                 ("ms_sort", f64), ("ms_index", f64), ("ms_forward", f64), ("ms_reverse", f64),
                 ("ms_refine", f64), ("launches", u64), ("rows_refined_fwd", u64),
                 ("rows_refined_rev", u64), ("rows_ambiguous", u64), ("evals_fwd", u64),
-                ("evals_rev", u64), ("sin_model", u64)]
+                ("evals_rev", u64), ("sin_model", u64), ("ms_host", f64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "grid"}

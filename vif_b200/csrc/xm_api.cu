@@ -6,6 +6,7 @@
 //   forward ring search (cat1 rows over cat2 cells), reverse ring search (cat2 rows over cat1)
 // There is no CPU fallback anywhere in this file: without a usable device every entry point
 // returns XM_ERR_CUDA.
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -116,7 +117,7 @@ double ord2f(unsigned long long o) {
 }
 
 struct SortedCat {
-    Scratch x, y, c, perm, key, cell;
+    Scratch rec, cell;
     CatView view{};
 };
 
@@ -124,32 +125,28 @@ struct SortedCat {
 int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
                     uint32_t ncell, SortedCat& out, cudaStream_t s, Error& err, uint64_t* launches,
                     cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
-    Scratch tmpk, tmpv, sscr;
-    XM_CUDA_TRY(out.x.alloc((size_t)n*8, s));
-    XM_CUDA_TRY(out.y.alloc((size_t)n*8, s));
-    XM_CUDA_TRY(out.c.alloc((size_t)n*8, s));
-    XM_CUDA_TRY(out.perm.alloc((size_t)n*4, s));
-    XM_CUDA_TRY(out.key.alloc((size_t)n*4, s));
+    Scratch key, perm, tmpk, tmpv, sscr;
+    XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
     XM_CUDA_TRY(out.cell.alloc((size_t)ncell*sizeof(uint2), s));
+    XM_CUDA_TRY(key.alloc((size_t)n*4, s));
+    XM_CUDA_TRY(perm.alloc((size_t)n*4, s));
     XM_CUDA_TRY(tmpk.alloc((size_t)n*4, s));
     XM_CUDA_TRY(tmpv.alloc((size_t)n*4, s));
     XM_CUDA_TRY(sscr.alloc(sort_scratch_bytes(n), s));
-    int32_t rc = launch_keys(ra, dec, n, g, out.key.as<uint32_t>(), out.perm.as<uint32_t>(), s, err, launches);
+    int32_t rc = launch_keys(ra, dec, n, g, key.as<uint32_t>(), perm.as<uint32_t>(), s, err, launches);
     if (rc) return rc;
     if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
     int bits = 1;
     while (bits < 32 && (1ull << bits) < (uint64_t)ncell) ++bits;
-    rc = launch_sort_pairs(out.key.as<uint32_t>(), out.perm.as<uint32_t>(), tmpk.as<uint32_t>(),
+    rc = launch_sort_pairs(key.as<uint32_t>(), perm.as<uint32_t>(), tmpk.as<uint32_t>(),
                            tmpv.as<uint32_t>(), n, bits, sscr.p, s, err, launches);
     if (rc) return rc;
     if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
-    rc = launch_cells_and_gather(out.key.as<uint32_t>(), out.perm.as<uint32_t>(), ra, dec, n, ncell,
-                                 g.linear != 0, out.x.as<double>(), out.y.as<double>(),
-                                 out.c.as<double>(), out.cell.as<uint2>(), s, err, launches);
+    rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
+                                 g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint2>(), s, err,
+                                 launches);
     if (rc) return rc;
-    out.view.x = out.x.as<double>(); out.view.y = out.y.as<double>(); out.view.c = out.c.as<double>();
-    out.view.perm = out.perm.as<uint32_t>(); out.view.key = out.key.as<uint32_t>();
-    out.view.cell = out.cell.as<uint2>(); out.view.n = n;
+    out.view.rec = out.rec.as<Rec>(); out.view.cell = out.cell.as<uint2>(); out.view.n = n;
     return XM_OK;
 }
 
@@ -273,10 +270,19 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         const double my = fmax(fmax(fabs(G.rdec0), fabs(G.rdec1)), G.ddec);
         g.fzx = 1e-12*mx*unit; g.fzy = 1e-12*my*unit;
 
-        Scratch cmin;
+        g.cs_rad = G.cell_size*(XM_DPI/180.0/3600.0);
+        {   // filter-kernel bounds (xm_search_fast.cu): H = largest half coordinate difference
+            const double H = 1.5*fmax(g.wx, g.wy);
+            g.eps_lo = H*H/3.0 + 1e-14;
+            g.eps_hi = 1e-14;
+            g.stop_delta = g.cs_rad*(1e-9 + 2.0*H*H);
+        }
+        Scratch cmin, ccen;
         XM_CUDA_TRY(cmin.alloc((size_t)g.ndec*8, s));
+        XM_CUDA_TRY(ccen.alloc((size_t)g.ndec*8, s));
         g.cmin_row = cmin.as<double>();
-        if (!linear && (rc = launch_cmin_rows(g, cmin.as<double>(), s, err, &launches))) return rc;
+        g.ccen_row = ccen.as<double>();
+        if (!linear && (rc = launch_row_tables(g, cmin.as<double>(), ccen.as<double>(), s, err, &launches))) return rc;
 
         SortedCat s1, s2;
         if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, s1, s, err, &launches, ev[2], ev[3]))) return rc;
@@ -296,13 +302,35 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         // the shared-index shortcut (slot equality) only applies when the arrays are the same
         if (self && !same_cat)
             return fail(err, XM_ERR_INVALID_ARG, "self=true requires catalog 2 to be catalog 1 (same pointers)");
-        if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, nth_eff, n1, id, d, nullptr,
-                                           (uint32_t)n1, false, ctx->d_ctr, s, err, &launches))) return rc;
+        // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
+        // the rows it flags (list length stays on the device: no host round trip)
+        const bool fast = !P.exact_only && fast_path_applicable(g);
+        Scratch refine;
+        if (fast) XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
+        if (fast && nth_eff == 1) {
+            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, refine.as<uint32_t>(),
+                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
+            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, 1u, n1, id, d, refine.as<uint32_t>(),
+                                               (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s,
+                                               err, &launches))) return rc;
+        } else {
+            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, nth_eff, n1, id, d, nullptr,
+                                               (uint32_t)n1, nullptr, false, ctx->d_ctr, s, err, &launches))) return rc;
+        }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
         if (mirror) {
             if (!self) {
-                if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd, nullptr,
-                                                   (uint32_t)n2, true, ctx->d_ctr, s, err, &launches))) return rc;
+                if (fast) {
+                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, refine.as<uint32_t>(),
+                                                    &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
+                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd,
+                                                       refine.as<uint32_t>(), (uint32_t)n2,
+                                                       &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err,
+                                                       &launches))) return rc;
+                } else {
+                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd, nullptr,
+                                                       (uint32_t)n2, nullptr, true, ctx->d_ctr, s, err, &launches))) return rc;
+                }
             } else {
                 // reverse pass skipped (qxmatch.hpp:395): rid = npos, rd = proxy_to_true(inf)
                 if ((rc = launch_fill_outputs(rid, rd, n2, linear ? dinf : dnan, s, err, &launches))) return rc;
@@ -399,7 +427,9 @@ int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const
         if (e != cudaSuccess) rc = fail_cuda(err, e, "cudaSetDevice", __FILE__, __LINE__);
         else {
             cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            const auto t0 = std::chrono::steady_clock::now();
             rc = run_device(ctx, s, ra1, dec1, n1, ra2, dec2, n2, *params, id, d, rid, rd, err);
+            ctx->last.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (rc == XM_ERR_CUDA) { cudaStreamSynchronize(s); cudaGetLastError(); }
         }
     }
@@ -421,6 +451,7 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
         DeviceGuard dg;
         XM_CUDA_TRY(dg.set(ctx->device));
         cudaStream_t s = ctx->stream;
+        const auto t0 = std::chrono::steady_clock::now();
         const uint64_t nth = params->nth < 1 ? 1 : params->nth;
         const bool mirror = !params->no_mirror;
         const bool same_cat = (ra1 == ra2 && dec1 == dec2 && n1 == n2);
@@ -447,6 +478,7 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
             XM_CUDA_TRY(cudaMemcpyAsync(rd, drd.p, n2*8, cudaMemcpyDeviceToHost, s));
         }
         XM_CUDA_TRY(cudaStreamSynchronize(s));
+        ctx->last.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return XM_OK;
     };
     rc = body();

@@ -14,15 +14,18 @@ namespace xm {
 #define XM_D2R (XM_DPI/180.0)
 
 // ---- device-side views ---------------------------------------------------------------------
-// One catalog sorted by cell key. x,y are radians (raw units when linear), c = cos(y).
+// One source of a catalog sorted by cell key: 32 bytes, fetched with a single LDG.256.
+// x,y are radians (raw units when linear), c = cos(y).
+struct __align__(32) Rec {
+    double   x, y, c;
+    uint32_t idx;           // original row of this source
+    uint32_t key;           // its cell key (ix*ndec + iy)
+};
+
 struct CatView {
-    const double*   x;
-    const double*   y;
-    const double*   c;
-    const uint32_t* perm;   // sorted position -> original row
-    const uint32_t* key;    // sorted cell keys (ix*ndec + iy)
-    const uint2*    cell;   // per cell: [begin, end) in sorted order (0,0 when empty)
-    uint32_t        n;
+    const Rec*   rec;       // sources in cell order (stable: ascending row inside a cell)
+    const uint2* cell;      // per cell: [begin, end) in sorted order (0,0 when empty)
+    uint32_t     n;
 };
 
 struct GridView {
@@ -33,6 +36,11 @@ struct GridView {
     double   fzx, fzy;        // slack on cell edges in search units: covers the rounding of the
                               // binning expression so that cell lower bounds stay rigorous
     const double* cmin_row;   // per cell row: lower bound of cos(dec) over the row (spherical)
+    const double* ccen_row;   // per cell row: cos(dec) of the row centre (filter kernel's stop rule)
+    double   cs_rad;          // cell_size in radians
+    double   eps_lo;          // filter metric Q vs 4*proxy: 4p in [Q(1-eps_lo), Q(1+eps_hi)]
+    double   eps_hi;
+    double   stop_delta;      // slack on the stop-rule radius [rad]
     uint32_t nra, ndec;
     uint32_t max_depth;       // max(nra, ndec): depth_cache::size(), qxmatch.hpp:85-87
     int32_t  linear;
@@ -73,8 +81,8 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
                     uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
-                                double* x, double* y, double* c, uint2* cell, cudaStream_t s,
-                                Error& err, uint64_t* launches);
+                                Rec* rec, uint2* cell, cudaStream_t s, Error& err,
+                                uint64_t* launches);
 // xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
 // by sort_scratch_bytes(n)
 size_t  sort_scratch_bytes(uint64_t n);
@@ -85,10 +93,18 @@ int32_t launch_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* tmp_keys, ui
 int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const CatView& cand,
                                  bool self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
-                                 uint32_t nrows, bool reverse, SearchCounters* ctr,
-                                 cudaStream_t s, Error& err, uint64_t* launches);
-int32_t launch_cmin_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err,
-                         uint64_t* launches);
+                                 uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
+                                 SearchCounters* ctr, cudaStream_t s, Error& err,
+                                 uint64_t* launches);
+int32_t launch_row_tables(const GridView& g, double* cmin_row, double* ccen_row, cudaStream_t s,
+                          Error& err, uint64_t* launches);
+// xm_search_fast.cu: nearest-neighbour filter kernel (nth = 1, spherical, rings 0-1); rows it cannot
+// decide rigorously are appended to refine_list (count in *refine_count) for the exact kernel
+bool    fast_path_applicable(const GridView& g);
+int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
+                              uint64_t* id_out, double* d_out, uint32_t* refine_list,
+                              unsigned long long* refine_count, bool reverse, SearchCounters* ctr,
+                              cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1, const double* c1,
                            uint32_t n1, const double* x2, const double* y2, const double* c2,
                            uint32_t n2, bool self, uint32_t nth_eff, uint64_t plane_stride,

@@ -92,8 +92,7 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
 __global__ void __launch_bounds__(kThreads)
 cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
                     const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
-                    int linear, double* __restrict__ x, double* __restrict__ y,
-                    double* __restrict__ c, uint2* __restrict__ cell) {
+                    int linear, Rec* __restrict__ rec, uint2* __restrict__ cell) {
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t k = skeys[p];
@@ -103,14 +102,16 @@ cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restri
     if (p + 1 == n || k != knext) cell[k].y = p + 1;
     const uint32_t i = perm[p];
     const double r = __ldg(ra + i), d = __ldg(dec + i);
+    Rec out;
+    out.idx = i; out.key = k;
     if (linear) {
-        x[p] = r; y[p] = d; c[p] = 1.0;
+        out.x = r; out.y = d; out.c = 1.0;
     } else {
-        const double yr = __dmul_rn(d, XM_D2R);
-        x[p] = __dmul_rn(r, XM_D2R);
-        y[p] = yr;
-        c[p] = cos(yr);
+        out.y = __dmul_rn(d, XM_D2R);
+        out.x = __dmul_rn(r, XM_D2R);
+        out.c = cos(out.y);
     }
+    rec[p] = out;
 }
 
 }  // namespace
@@ -138,11 +139,11 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
 
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
-                                double* x, double* y, double* c, uint2* cell, cudaStream_t s,
-                                Error& err, uint64_t* launches) {
+                                Rec* rec, uint2* cell, cudaStream_t s, Error& err,
+                                uint64_t* launches) {
     XM_CUDA_TRY(cudaMemsetAsync(cell, 0, (size_t)ncell*sizeof(uint2), s));
     cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
-                                                                        linear ? 1 : 0, x, y, c, cell);
+                                                                        linear ? 1 : 0, rec, cell);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;

@@ -41,6 +41,20 @@ __device__ __forceinline__ double sin_ref(double x, int model) {
     return sin(x);
 }
 
+// same, for callers that guarantee |x| < 0.126 (coordinates a few cells apart): no libm fallback
+__device__ __forceinline__ double sin_ref_small(double x, int model) {
+    if (fabs(x) < 0x1p-26) return x;
+    return sin_taylor_glibc(x, model);
+}
+
+__device__ __forceinline__ double proxy_sph_small(double x1, double y1, double c1, double x2,
+                                                  double y2, double c2, int model) {
+    const double sra = sin_ref_small(__dmul_rn(0.5, __dsub_rn(x2, x1)), model);
+    const double sde = sin_ref_small(__dmul_rn(0.5, __dsub_rn(y2, y1)), model);
+    return __dadd_rn(__dmul_rn(sde, sde),
+                     __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), c2), c1));
+}
+
 // qxmatch.hpp:200-202: sde*sde + sra*sra*dcdec2*dcdec1, left to right.
 __device__ __forceinline__ double proxy_sph(double x1, double y1, double c1, double x2, double y2,
                                             double c2, int model) {

@@ -108,12 +108,10 @@ __device__ __forceinline__ bool list_ambiguous(const List& L, uint32_t k_eff) {
     return amb;
 }
 
+// all 32 lanes of every warp must reach this (no early returns in the kernels)
 __device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned long long v) {
-    const unsigned m = __activemask();
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
-    if (m == 0xffffffffu) {
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
-    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
 // ---- rigorous lower bound of the proxy over one cell -----------------------------------------
@@ -144,8 +142,9 @@ template <class List, bool LINEAR>
 __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView& src,
                                                 const CatView& cand, bool self_mode, uint32_t p,
                                                 List& L, unsigned long long& evals) {
-    const double x1 = src.x[p], y1 = src.y[p], c1 = src.c[p];
-    const uint32_t key = src.key[p];
+    const Rec me = src.rec[p];
+    const double x1 = me.x, y1 = me.y, c1 = me.c;
+    const uint32_t key = me.key;
     const int64_t x0 = key/g.ndec, y0 = key - (uint32_t)x0*g.ndec;
 
     // distance of the source from its cell centre (qxmatch.hpp:298-299)
@@ -171,9 +170,9 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
             if (d > 0 && cell_lower_bound<LINEAR>(g, x1, y1, c1, cx, cy) >= L.kth()) return;
             for (uint32_t q = r.x; q < r.y; ++q) {
                 if (self_mode && q == p) continue;
-                const double sd = LINEAR ? proxy_lin(x1, y1, cand.x[q], cand.y[q])
-                                         : proxy_sph(x1, y1, c1, cand.x[q], cand.y[q], cand.c[q],
-                                                     g.sin_model);
+                const Rec cd = cand.rec[q];
+                const double sd = LINEAR ? proxy_lin(x1, y1, cd.x, cd.y)
+                                         : proxy_sph(x1, y1, c1, cd.x, cd.y, cd.c, g.sin_model);
                 ++evals;
                 L.insert(sd, q);
             }
@@ -193,12 +192,16 @@ __global__ void __launch_bounds__(kRingThreads)
 ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, uint32_t nth_eff,
                          uint64_t plane_stride, uint64_t* __restrict__ id_out,
                          double* __restrict__ d_out, const uint32_t* __restrict__ rows,
-                         uint32_t nrows, int reverse, SearchCounters* ctr) {
-    const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
+                         uint32_t nrows, const unsigned long long* __restrict__ nrows_dev,
+                         int reverse, SearchCounters* ctr) {
+    // rows == nullptr: thread t handles sorted slot t. Otherwise the kernel walks the row list with
+    // a grid-stride loop; its length may live on the device (filter kernel's refine count).
+    if (nrows_dev) { const unsigned long long c = *nrows_dev; nrows = c < nrows ? (uint32_t)c : nrows; }
     unsigned long long evals = 0, amb = 0;
-    if (t < nrows) {
+    const uint32_t stride = gridDim.x*blockDim.x;
+    for (uint32_t t = blockIdx.x*blockDim.x + threadIdx.x; t < nrows; t += stride) {
         const uint32_t p = rows ? rows[t] : t;
-        const uint32_t i = src.perm[p];
+        const uint32_t i = src.rec[p].idx;
         if (K > 0) {
             RegList<(K > 0 ? K : 1)> L;
             L.init();
@@ -206,20 +209,20 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
 #pragma unroll
             for (int k = 0; k < (K > 0 ? K : 1); ++k) {
                 const uint32_t q = L.q[k];
-                id_out[(uint64_t)k*plane_stride + i] = q == kNoCand ? XM_NPOS : (uint64_t)cand.perm[q];
+                id_out[(uint64_t)k*plane_stride + i] = q == kNoCand ? XM_NPOS : (uint64_t)cand.rec[q].idx;
                 d_out[(uint64_t)k*plane_stride + i] = proxy_to_true(L.d[k], LINEAR);
             }
-            amb = list_ambiguous(L, (uint32_t)(K > 0 ? K : 1)) ? 1 : 0;
+            amb += list_ambiguous(L, (uint32_t)(K > 0 ? K : 1)) ? 1 : 0;
         } else {
             MemList L;
             L.d = d_out + i; L.q = id_out + i; L.stride = plane_stride; L.k_eff = nth_eff;
             L.init();
             ring_search_row<MemList, LINEAR>(g, src, cand, self_mode != 0, p, L, evals);
-            amb = list_ambiguous(L, nth_eff) ? 1 : 0;
+            amb += list_ambiguous(L, nth_eff) ? 1 : 0;
             for (uint32_t k = 0; k < nth_eff; ++k) {
                 const uint32_t q = L.get_q(k);
                 const double pd = L.get_d(k);
-                id_out[(uint64_t)k*plane_stride + i] = q == kNoCand ? XM_NPOS : (uint64_t)cand.perm[q];
+                id_out[(uint64_t)k*plane_stride + i] = q == kNoCand ? XM_NPOS : (uint64_t)cand.rec[q].idx;
                 d_out[(uint64_t)k*plane_stride + i] = proxy_to_true(pd, LINEAR);
             }
         }
@@ -311,8 +314,9 @@ __global__ void fill_outputs_kernel(uint64_t* __restrict__ id, double* __restric
     }
 }
 
-// lower bound of cos(dec) over each cell row, -1 where the row is not inside [-pi/2, pi/2]
-__global__ void cmin_rows_kernel(GridView g, double* __restrict__ out) {
+// per cell row: lower bound of cos(dec) over the row (-1 where the row is not inside
+// [-pi/2, pi/2]) and cos(dec) at the row centre
+__global__ void row_tables_kernel(GridView g, double* __restrict__ cmin, double* __restrict__ ccen) {
     const uint32_t cy = blockIdx.x*blockDim.x + threadIdx.x;
     if (cy >= g.ndec) return;
     const double lo = g.oy + (double)cy*g.wy - g.fzy, hi = lo + g.wy + 2.0*g.fzy;
@@ -322,19 +326,22 @@ __global__ void cmin_rows_kernel(GridView g, double* __restrict__ out) {
         v = fmin(cos(lo), cos(hi))*(1.0 - 1e-12) - 1e-15;
         if (v < 0.0) v = 0.0;
     }
-    out[cy] = v;
+    cmin[cy] = v;
+    // centre declination as the reference computes it (qxmatch.hpp:299), then to radians
+    const double cdeg = __dadd_rn(g.rdec0, __dmul_rn(__dadd_rn((double)cy, 0.5), g.ddec));
+    ccen[cy] = cos(__dmul_rn(XM_D2R, cdeg));
 }
 
 template <bool LINEAR>
 void dispatch_ring(int K, dim3 grid, cudaStream_t s, const GridView& g, const CatView& src,
                    const CatView& cand, int self_mode, uint32_t nth_eff, uint64_t stride,
-                   uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows, int reverse,
-                   SearchCounters* ctr) {
+                   uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows,
+                   const unsigned long long* nrows_dev, int reverse, SearchCounters* ctr) {
 #define XM_CASE(KK) case KK: ring_search_exact_kernel<KK, LINEAR><<<grid, kRingThreads, 0, s>>>( \
-        g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, reverse, ctr); break;
+        g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, ctr); break;
     switch (K) { XM_CASE(1) XM_CASE(2) XM_CASE(3) XM_CASE(4) XM_CASE(5) XM_CASE(6) XM_CASE(7) XM_CASE(8)
                  default: ring_search_exact_kernel<0, LINEAR><<<grid, kRingThreads, 0, s>>>(
-                     g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, reverse, ctr); }
+                     g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, ctr); }
 #undef XM_CASE
 }
 
@@ -359,15 +366,18 @@ void dispatch_brute(int K, dim3 grid, cudaStream_t s, int sin_model, const doubl
 int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const CatView& cand,
                                  bool self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
-                                 uint32_t nrows, bool reverse, SearchCounters* ctr,
-                                 cudaStream_t s, Error& err, uint64_t* launches) {
+                                 uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
+                                 SearchCounters* ctr, cudaStream_t s, Error& err,
+                                 uint64_t* launches) {
     if (nrows == 0 || nth_eff == 0) return XM_OK;
-    const dim3 grid((nrows + kRingThreads - 1)/kRingThreads);
+    uint32_t blocks = (nrows + kRingThreads - 1)/kRingThreads;
+    if (nrows_dev && blocks > 148*4) blocks = 148*4;     // list of unknown (small) length: persistent grid
+    const dim3 grid(blocks);
     const int K = nth_eff <= 8 ? (int)nth_eff : 0;
     if (g.linear) dispatch_ring<true>(K, grid, s, g, src, cand, self, nth_eff, plane_stride, id_out,
-                                      d_out, rows, nrows, reverse, ctr);
+                                      d_out, rows, nrows, nrows_dev, reverse, ctr);
     else dispatch_ring<false>(K, grid, s, g, src, cand, self, nth_eff, plane_stride, id_out, d_out,
-                              rows, nrows, reverse, ctr);
+                              rows, nrows, nrows_dev, reverse, ctr);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
@@ -412,9 +422,9 @@ int32_t launch_fill_outputs(uint64_t* id, double* d, uint64_t n, double dval, cu
     return XM_OK;
 }
 
-int32_t launch_cmin_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err,
-                         uint64_t* launches) {
-    cmin_rows_kernel<<<(g.ndec + 255)/256, 256, 0, s>>>(g, cmin_row);
+int32_t launch_row_tables(const GridView& g, double* cmin_row, double* ccen_row, cudaStream_t s,
+                          Error& err, uint64_t* launches) {
+    row_tables_kernel<<<(g.ndec + 255)/256, 256, 0, s>>>(g, cmin_row, ccen_row);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
