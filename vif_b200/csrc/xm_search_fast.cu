@@ -49,72 +49,139 @@ __device__ __forceinline__ Rec load_rec(const Rec* p) {
     return r;
 }
 
+// Running state of one source. Q >= 0, so the high 32 bits of its IEEE pattern are a monotone
+// 21-bit-mantissa image of it: the loop tracks the smallest and second smallest HIGH WORDS with
+// native 32-bit integer min/max (FP64 min/max are multi-instruction selects on sm_100) and the slot
+// of the smallest. Two metrics with different high words are strictly ordered; metrics sharing a
+// high word (within 2^-20 of each other) are told apart by the exact kernel.
 struct Best {
-    double q1, q2;        // smallest and second smallest filter metric
-    double x, y, c;       // coordinates of the current winner
-    uint32_t idx;
+    int32_t h1, h2;
+    uint32_t slot;
 };
 
-__device__ __forceinline__ void scan_cell(const Rec* __restrict__ rec, uint2 r, double x1, double y1,
-                                          double c1, uint32_t skip, Best& b, uint32_t& evals) {
-    for (uint32_t q = r.x; q < r.y; ++q) {
-        const Rec cd = load_rec(rec + q);
-        const double dx = cd.x - x1, dy = cd.y - y1;
-        double Q = fma(dx*dx*cd.c, c1, dy*dy);
-        if (q == skip) Q = dinf();                       // self match: never pair a source with itself
-        if (Q < b.q2) {
-            if (Q < b.q1) {
-                b.q2 = b.q1; b.q1 = Q; b.x = cd.x; b.y = cd.y; b.c = cd.c; b.idx = cd.idx;
-            } else if (!(Q == b.q1 && cd.x == b.x && cd.y == b.y)) {
-                b.q2 = Q;                                // identical coordinates: exact tie, first stays
-            }
-        }
+constexpr int32_t kInfHi = 0x7ff00000;
+
+// smallest / largest double whose high word is h
+__device__ __forceinline__ double hi_floor(int32_t h) { return __hiloint2double(h, 0); }
+__device__ __forceinline__ double hi_ceil(int32_t h) {
+    return h >= kInfHi ? __hiloint2double(kInfHi, 0) : __hiloint2double(h + 1, 0);
+}
+
+template <bool SELF>
+__device__ __forceinline__ void eval_loaded(const Rec& cd, uint32_t q, double x1, double y1, double c1,
+                                            uint32_t self_slot, Best& b) {
+    const double dx = cd.x - x1, dy = cd.y - y1;
+    const double Q = fma(dx*dx*cd.c, c1, dy*dy);
+    int32_t h = __double2hiint(Q);
+    if (SELF && q == self_slot) h = kInfHi;             // never pair a source with itself
+    const bool better = h < b.h1;
+    b.h2 = min(b.h2, max(b.h1, h));
+    b.h1 = min(b.h1, h);
+    b.slot = better ? q : b.slot;
+}
+
+// all candidates of one cell; four independent 32-byte loads in flight per step
+template <bool SELF>
+__device__ __forceinline__ void scan_range(const Rec* __restrict__ rec, uint32_t qs, uint32_t qe,
+                                           double x1, double y1, double c1, uint32_t self_slot,
+                                           Best& b) {
+    uint32_t q = qs;
+    for (; q + 4 <= qe; q += 4) {
+        const Rec r0 = load_rec(rec + q), r1 = load_rec(rec + q + 1);
+        const Rec r2 = load_rec(rec + q + 2), r3 = load_rec(rec + q + 3);
+        eval_loaded<SELF>(r0, q, x1, y1, c1, self_slot, b);
+        eval_loaded<SELF>(r1, q + 1, x1, y1, c1, self_slot, b);
+        eval_loaded<SELF>(r2, q + 2, x1, y1, c1, self_slot, b);
+        eval_loaded<SELF>(r3, q + 3, x1, y1, c1, self_slot, b);
     }
-    evals += r.y - r.x;
+    if (q + 2 <= qe) {
+        const Rec r0 = load_rec(rec + q), r1 = load_rec(rec + q + 1);
+        eval_loaded<SELF>(r0, q, x1, y1, c1, self_slot, b);
+        eval_loaded<SELF>(r1, q + 1, x1, y1, c1, self_slot, b);
+        q += 2;
+    }
+    if (q < qe) {
+        const Rec r0 = load_rec(rec + q);
+        eval_loaded<SELF>(r0, q, x1, y1, c1, self_slot, b);
+    }
 }
 
 // 0: stop for certain, 1: continue for certain, 2: inside the slack
-__device__ __forceinline__ int stop_decision(double q1, double tr, const GridView& g) {
+// (q1 is only known to lie in [q1_lo, q1_hi))
+__device__ __forceinline__ int stop_decision(double q1_lo, double q1_hi, double tr, const GridView& g) {
     const double lo = tr - g.stop_delta, hi = tr + g.stop_delta;
-    if (lo > 0.0 && q1*(1.0 + g.eps_hi) <= lo*lo*(1.0 - lo*lo*(1.0/12.0) - 1e-12)) return 0;
-    if (hi <= 0.0) return q1 > 0.0 ? 1 : 2;
-    if (q1*(1.0 - g.eps_lo) > hi*hi) return 1;
+    if (lo > 0.0 && q1_hi*(1.0 + g.eps_hi) <= lo*lo*(1.0 - lo*lo*(1.0/12.0) - 1e-12)) return 0;
+    if (hi <= 0.0) return q1_lo > 0.0 ? 1 : 2;
+    if (q1_lo*(1.0 - g.eps_lo) > hi*hi) return 1;
     return 2;
 }
 
-__global__ void __launch_bounds__(kThreads)
-ring_nn_filter_kernel(GridView g, CatView src, CatView cand, int self_mode,
-                      uint64_t* __restrict__ id_out, double* __restrict__ d_out,
-                      uint32_t* __restrict__ refine_list, unsigned long long* refine_count,
-                      int reverse, SearchCounters* ctr) {
+// merge the (smallest, second smallest, slot) triple of another candidate set into b
+__device__ __forceinline__ void merge_best(Best& b, int32_t a1, int32_t a2, uint32_t aslot) {
+    const bool better = a1 < b.h1;
+    b.h2 = min(min(b.h2, a2), max(b.h1, a1));
+    b.h1 = min(b.h1, a1);
+    b.slot = better ? aslot : b.slot;
+}
+
+constexpr int kMaxItems = 4*kThreads;    // ring-1 work items a CTA can queue (4 per source; typical total ~90)
+
+// Work shape of one CTA (128 consecutive sources in cell order):
+//   1. every thread scans its source's own cell (ring 0), applies the stop rule and derives the
+//      bitmask of ring-1 cells that survive the culling test;
+//   2. the surviving (source, cell) pairs are queued in shared memory (block-wide prefix sum), so
+//      that
+//   3. the CTA's threads take one queued pair each -- a source that needs three neighbouring cells
+//      no longer stalls the 31 lanes next to it that need none;
+//   4. every thread merges the partial results of its own source, applies the stop rule of ring 1
+//      and the ambiguity test, and writes id / d (or queues the row for the exact kernel).
+template <bool SELF>
+__global__ void __launch_bounds__(kThreads, 8)
+ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restrict__ id_out,
+                      double* __restrict__ d_out, uint32_t* __restrict__ refine_list,
+                      unsigned long long* refine_count, int reverse, SearchCounters* ctr) {
+    __shared__ double s_x[kThreads], s_y[kThreads], s_c[kThreads];
+    __shared__ uint8_t  s_owner[kMaxItems];             // thread that owns the queued (source, cell) pair
+    __shared__ uint2    s_range[kMaxItems];             // candidate slots of the cell
+    __shared__ int32_t  s_a1[kMaxItems], s_a2[kMaxItems];
+    __shared__ uint32_t s_slot[kMaxItems];
+    __shared__ uint32_t s_warp_tot[kThreads/32];
+
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool live = p < src.n;
     uint32_t evals = 0;
-    if (p < src.n) {
-        const Rec me = load_rec(src.rec + p);
+
+    Rec me;
+    me.x = me.y = me.c = 0.0; me.idx = 0; me.key = 0;
+    Best b;
+    b.h1 = kInfHi; b.h2 = kInfHi; b.slot = 0xffffffffu;
+    bool flag = false, done = !live;
+    uint32_t mask = 0;
+    int x0 = 0, y0 = 0;
+    double cdist = 0.0;
+
+    if (live) {
+        me = load_rec(src.rec + p);
+        x0 = (int)(me.key/g.ndec); y0 = (int)(me.key - (uint32_t)x0*g.ndec);
         const double x1 = me.x, y1 = me.y, c1 = me.c;
-        const int x0 = (int)(me.key/g.ndec), y0 = (int)(me.key - (uint32_t)x0*g.ndec);
-        const uint32_t skip = self_mode ? p : 0xffffffffu;
-        const int ndec = (int)g.ndec, nra = (int)g.nra;
-
-        Best b;
-        b.q1 = dinf(); b.q2 = dinf(); b.x = 0; b.y = 0; b.c = 0; b.idx = 0xffffffffu;
-        bool flag = false, done = false;
-
         // ---- ring 0: own cell ------------------------------------------------------------------
-        scan_cell(cand.rec, cand.cell[me.key], x1, y1, c1, skip, b, evals);
-
+        {
+            const uint2 r = cand.cell[me.key];
+            scan_range<SELF>(cand.rec, r.x, r.y, x1, y1, c1, p, b);
+            evals += r.y - r.x;
+        }
         // distance to the cell centre and the stop rule after ring 0 (max_dist = cs/2)
         const double ex_lo = g.ox + (double)x0*g.wx, ey_lo = g.oy + (double)y0*g.wy;
         const double dxc = (ex_lo + 0.5*g.wx) - x1, dyc = (ey_lo + 0.5*g.wy) - y1;
-        const double cdist = sqrt(fma(dxc*dxc*g.ccen_row[y0], c1, dyc*dyc));
+        cdist = sqrt(fma(dxc*dxc*g.ccen_row[y0], c1, dyc*dyc));
         {
-            const int dec = stop_decision(b.q1, 0.4*g.cs_rad - 1.1*cdist, g);
+            const int dec = stop_decision(hi_floor(b.h1), hi_ceil(b.h1), 0.4*g.cs_rad - 1.1*cdist, g);
             if (dec == 0) done = true; else if (dec == 2) { flag = true; done = true; }
         }
-
         if (!done) {
-            // ---- ring 1: the other 24 cells of the 5x5 block ----------------------------------------
-            // squared gaps from the source to the block's cell columns/rows (with the binning slack)
+            // ---- ring 1: which of the other 24 cells of the 5x5 block can hold a winner? ---------
+            const int ndec = (int)g.ndec, nra = (int)g.nra;
             double gl = x1 - ex_lo - g.fzx, gr = (ex_lo + g.wx) - x1 - g.fzx;
             double gd = y1 - ey_lo - g.fzy, gu = (ey_lo + g.wy) - y1 - g.fzy;
             gl = gl > 0 ? gl : 0; gr = gr > 0 ? gr : 0; gd = gd > 0 ? gd : 0; gu = gu > 0 ? gu : 0;
@@ -122,67 +189,116 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, int self_mode,
             double GX[5], GY[5], CM[5];
             GX[2] = 0.0; GX[3] = gr*gr*c1; GX[4] = (gr + g.wx)*(gr + g.wx)*c1;
             GX[1] = gl*gl*c1; GX[0] = (gl + g.wx)*(gl + g.wx)*c1;
-            GY[2] = 0.0; GY[3] = gu*gu; GY[4] = (gu + g.wy)*(gu + g.wy);
-            GY[1] = gd*gd; GY[0] = (gd + g.wy)*(gd + g.wy);
+            GY[2] = 0.0; GY[3] = gu*gu*shrink; GY[4] = (gu + g.wy)*(gu + g.wy)*shrink;
+            GY[1] = gd*gd*shrink; GY[0] = (gd + g.wy)*(gd + g.wy)*shrink;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const int yy = y0 + k - 2;
                 CM[k] = (yy >= 0 && yy < ndec) ? g.cmin_row[yy]*shrink : -1.0;
-                GY[k] *= shrink;
             }
-            // three phases (sides, corners, outer cells): survivors are re-derived from the current
-            // best before each phase, then scanned by a per-lane loop over the set bits
+            const double thr = hi_ceil(b.h1)*(1.0 + g.eps_hi)*(1.0 + 1e-9);
 #pragma unroll
-            for (int phase = 0; phase < 3; ++phase) {
-                const int e0 = phase == 0 ? 0 : (phase == 1 ? 4 : 8);
-                const int e1 = phase == 0 ? 4 : (phase == 1 ? 8 : 24);
-                const double thr = b.q1*(1.0 + g.eps_hi)*(1.0 + 1e-9);
-                uint32_t mask = 0;
-#pragma unroll
-                for (int e = e0; e < e1; ++e) {
-                    constexpr int8_t BX[24] = {0, 1, 0, -1, 1, -1, -1, 1,
-                                               0, 1, 2, 2, 2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1};
-                    constexpr int8_t BY[24] = {1, 0, -1, 0, 1, 1, -1, -1,
-                                               2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1, 0, 1, 2, 2};
-                    const int bx = BX[e], by = BY[e];
-                    const int cx = x0 + bx;
-                    const double cm = CM[by + 2];
-                    // cm < 0: row outside the grid or beyond a pole -> outside: skip, pole: flag below
-                    const double lb = fma(GX[bx + 2], cm, GY[by + 2]);
-                    const bool in_grid = cx >= 0 && cx < nra && cm >= 0.0;
-                    if (in_grid && lb < thr) mask |= 1u << e;
-                }
-                while (mask) {
-                    const int e = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const uint32_t cell = (uint32_t)(x0 + c_bx[e])*g.ndec + (uint32_t)(y0 + c_by[e]);
-                    const uint2 r = cand.cell[cell];
-                    if (r.x != r.y) scan_cell(cand.rec, r, x1, y1, c1, skip, b, evals);
-                }
+            for (int e = 0; e < 24; ++e) {
+                constexpr int8_t BX[24] = {0, 1, 0, -1, 1, -1, -1, 1,
+                                           0, 1, 2, 2, 2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1};
+                constexpr int8_t BY[24] = {1, 0, -1, 0, 1, 1, -1, -1,
+                                           2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1, 0, 1, 2, 2};
+                const int bx = BX[e], by = BY[e];
+                const int cx = x0 + bx;
+                const double cm = CM[by + 2];
+                const double lb = fma(GX[bx + 2], cm, GY[by + 2]);
+                if (cx >= 0 && cx < nra && cm >= 0.0 && lb < thr) mask |= 1u << e;
             }
+        }
+    }
+
+    // ---- queue the surviving (source, cell) pairs ------------------------------------------------
+    // The owner fetches the cells' candidate ranges itself (independent loads, issued back to back)
+    // and queues only non-empty cells, so the thread that later takes a pair starts on the
+    // candidates right away.
+    s_x[threadIdx.x] = me.x; s_y[threadIdx.x] = me.y; s_c[threadIdx.x] = me.c;
+    uint2 rng[4];
+    uint32_t cnt = 0;
+    bool spill = false;                                 // more than 4 non-empty cells: scan in place
+    {
+        uint32_t m = mask;
+        while (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            const uint2 r = cand.cell[(uint32_t)((int)me.key + (int)c_bx[e]*(int)g.ndec + (int)c_by[e])];
+            if (r.x == r.y) continue;
+            if (cnt < 4) {
+                // static indexing keeps rng[] in registers
+                if (cnt == 0) rng[0] = r; else if (cnt == 1) rng[1] = r; else if (cnt == 2) rng[2] = r; else rng[3] = r;
+                ++cnt;
+            } else {
+                spill = true;
+                scan_range<SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, p, b);
+                evals += r.y - r.x;
+            }
+        }
+    }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t first = inc - cnt, total = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads/32; ++k) {
+        if (k < wid) first += s_warp_tot[k];
+        total += s_warp_tot[k];
+    }
+    // total <= 4*kThreads <= kMaxItems by construction
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if ((uint32_t)k < cnt) { s_owner[first + k] = (uint8_t)threadIdx.x; s_range[first + k] = rng[k]; }
+    }
+    __syncthreads();
+
+    // ---- one queued pair per thread ----------------------------------------------------------------
+    for (uint32_t it = threadIdx.x; it < total; it += kThreads) {
+        const int owner = s_owner[it];
+        const uint2 r = s_range[it];
+        Best a;
+        a.h1 = kInfHi; a.h2 = kInfHi; a.slot = 0xffffffffu;
+        scan_range<SELF>(cand.rec, r.x, r.y, s_x[owner], s_y[owner], s_c[owner],
+                         blockIdx.x*blockDim.x + owner, a);
+        evals += r.y - r.x;
+        s_a1[it] = a.h1; s_a2[it] = a.h2; s_slot[it] = a.slot;
+    }
+    __syncthreads();
+    for (uint32_t k = 0; k < cnt; ++k) merge_best(b, s_a1[first + k], s_a2[first + k], s_slot[first + k]);
+    (void)spill;
+
+    if (live) {
+        if (!done) {
             // stop rule after ring 1 (max_dist = 2.5 cs): going on to ring 2 is the exact kernel's job
-            const int dec = stop_decision(b.q1, 2.4*g.cs_rad - 1.1*cdist, g);
+            const int dec = stop_decision(hi_floor(b.h1), hi_ceil(b.h1), 2.4*g.cs_rad - 1.1*cdist, g);
             if (dec != 0) flag = true;
         }
-
-        // the winner must beat the runner-up by more than the filter's uncertainty
-        if (!(b.q1*(1.0 + g.eps_hi) < b.q2*(1.0 - g.eps_lo)) && b.q2 < dinf()) flag = true;
-        if (b.idx == 0xffffffffu) flag = true;
+        // the winner must beat the runner-up by more than the filter's uncertainty (including the
+        // truncation to high words)
+        if (b.h2 < kInfHi && !(hi_ceil(b.h1)*(1.0 + g.eps_hi) < hi_floor(b.h2)*(1.0 - g.eps_lo))) flag = true;
+        if (b.slot == 0xffffffffu) flag = true;
 
         if (flag) {
-            const unsigned long long slot = atomicAdd(refine_count, 1ull);
-            refine_list[slot] = p;
+            const unsigned long long pos = atomicAdd(refine_count, 1ull);
+            refine_list[pos] = p;
         } else {
             // exact proxy of the winning pair in reference-order arithmetic -> arcsec
-            const double pr = proxy_sph_small(x1, y1, c1, b.x, b.y, b.c, g.sin_model);
-            id_out[me.idx] = (uint64_t)b.idx;
+            const Rec w = load_rec(cand.rec + b.slot);
+            const double pr = proxy_sph_small(me.x, me.y, me.c, w.x, w.y, w.c, g.sin_model);
+            id_out[me.idx] = (uint64_t)w.idx;
             d_out[me.idx] = proxy_to_true(pr, false);
         }
     }
-    __syncwarp();
     unsigned long long v = evals;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, v);
+    if (lane == 0 && v) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, v);
 }
 
 }  // namespace
@@ -203,8 +319,11 @@ int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatVi
                               unsigned long long* refine_count, bool reverse, SearchCounters* ctr,
                               cudaStream_t s, Error& err, uint64_t* launches) {
     if (src.n == 0) return XM_OK;
-    ring_nn_filter_kernel<<<(src.n + kThreads - 1)/kThreads, kThreads, 0, s>>>(
-        g, src, cand, self ? 1 : 0, id_out, d_out, refine_list, refine_count, reverse ? 1 : 0, ctr);
+    const dim3 grid((src.n + kThreads - 1)/kThreads);
+    if (self) ring_nn_filter_kernel<true><<<grid, kThreads, 0, s>>>(g, src, cand, id_out, d_out, refine_list,
+                                                                   refine_count, reverse ? 1 : 0, ctr);
+    else ring_nn_filter_kernel<false><<<grid, kThreads, 0, s>>>(g, src, cand, id_out, d_out, refine_list,
+                                                                refine_count, reverse ? 1 : 0, ctr);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
