@@ -88,6 +88,16 @@ def test_clustered_self(oracle, levels, nth):
         assert np.sum(exp["id"][0] == exp["id"][1]) > 0      # the quirk is present and reproduced
 
 
+def test_self_with_distinct_arrays(oracle):
+    """self=true with two separate (equal) arrays is legal in the reference: row i skips j == i."""
+    ra, dec = G.c1(23, 20_000)
+    exp = oracle.oracle_qxmatch(ra, dec, ra.copy(), dec.copy(), thread=4, nth=2, self=True)
+    got = qxmatch(ra, dec, ra.copy(), dec.copy(), nth=2, self=True)
+    assert_same_result(got, exp, RTOL, "self-distinct")
+    got1 = qxmatch(ra, dec, ra.copy(), dec.copy(), self=True)
+    assert np.array_equal(got1.id[0], exp["id"][0])
+
+
 def test_errors_nonfinite_and_grid():
     a = np.array([0.1, np.nan, 0.3]); b = np.array([0.1, 0.2, 0.3])
     with pytest.raises(QxmatchError, match="first RA and Dec coordinates contain invalid values"):

@@ -300,21 +300,20 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         }
         // `self` with two different arrays is legal in the reference (i == j skipped by index);
         // the shared-index shortcut (slot equality) only applies when the arrays are the same
-        if (self && !same_cat)
-            return fail(err, XM_ERR_INVALID_ARG, "self=true requires catalog 2 to be catalog 1 (same pointers)");
+        const int self_mode = self ? (same_cat ? 1 : 2) : 0;
         // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
         // the rows it flags (list length stays on the device: no host round trip)
-        const bool fast = !P.exact_only && fast_path_applicable(g);
+        const bool fast = !P.exact_only && fast_path_applicable(g) && self_mode != 2;
         Scratch refine;
         if (fast) XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
         if (fast && nth_eff == 1) {
             if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
-            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, 1u, n1, id, d, refine.as<uint32_t>(),
+            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
                                                (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s,
                                                err, &launches))) return rc;
         } else {
-            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self, nth_eff, n1, id, d, nullptr,
+            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, nth_eff, n1, id, d, nullptr,
                                                (uint32_t)n1, nullptr, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
@@ -323,12 +322,12 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
                 if (fast) {
                     if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, refine.as<uint32_t>(),
                                                     &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
-                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd,
+                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
                                                        refine.as<uint32_t>(), (uint32_t)n2,
                                                        &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err,
                                                        &launches))) return rc;
                 } else {
-                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, false, 1u, n2, rid, rd, nullptr,
+                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd, nullptr,
                                                        (uint32_t)n2, nullptr, true, ctx->d_ctr, s, err, &launches))) return rc;
                 }
             } else {

@@ -90,8 +90,9 @@ int32_t launch_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* tmp_keys, ui
                           uint32_t n, int key_bits, void* scratch, cudaStream_t s, Error& err,
                           uint64_t* launches);
 // xm_search_exact.cu: reference-order arithmetic (compiled with -fmad=false)
+// self: 0 = off, 1 = both views are the same index (skip equal slots), 2 = skip equal original rows
 int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const CatView& cand,
-                                 bool self, uint32_t nth_eff, uint64_t plane_stride,
+                                 int self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
                                  uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
                                  SearchCounters* ctr, cudaStream_t s, Error& err,

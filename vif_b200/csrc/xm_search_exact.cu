@@ -140,7 +140,7 @@ __device__ __forceinline__ double cell_lower_bound(const GridView& g, double x1,
 // ---- ring search ---------------------------------------------------------------------------------
 template <class List, bool LINEAR>
 __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView& src,
-                                                const CatView& cand, bool self_mode, uint32_t p,
+                                                const CatView& cand, int self_mode, uint32_t p,
                                                 List& L, unsigned long long& evals) {
     const Rec me = src.rec[p];
     const double x1 = me.x, y1 = me.y, c1 = me.c;
@@ -169,8 +169,11 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
             if (r.x == r.y) return;
             if (d > 0 && cell_lower_bound<LINEAR>(g, x1, y1, c1, cx, cy) >= L.kth()) return;
             for (uint32_t q = r.x; q < r.y; ++q) {
-                if (self_mode && q == p) continue;
+                // self match (qxmatch.hpp:314): skip the source itself -- same slot when both
+                // catalogs share one index (1), same original row otherwise (2)
+                if (self_mode == 1 && q == p) continue;
                 const Rec cd = cand.rec[q];
+                if (self_mode == 2 && cd.idx == me.idx) continue;
                 const double sd = LINEAR ? proxy_lin(x1, y1, cd.x, cd.y)
                                          : proxy_sph(x1, y1, c1, cd.x, cd.y, cd.c, g.sin_model);
                 ++evals;
@@ -205,7 +208,7 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
         if (K > 0) {
             RegList<(K > 0 ? K : 1)> L;
             L.init();
-            ring_search_row<RegList<(K > 0 ? K : 1)>, LINEAR>(g, src, cand, self_mode != 0, p, L, evals);
+            ring_search_row<RegList<(K > 0 ? K : 1)>, LINEAR>(g, src, cand, self_mode, p, L, evals);
 #pragma unroll
             for (int k = 0; k < (K > 0 ? K : 1); ++k) {
                 const uint32_t q = L.q[k];
@@ -217,7 +220,7 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
             MemList L;
             L.d = d_out + i; L.q = id_out + i; L.stride = plane_stride; L.k_eff = nth_eff;
             L.init();
-            ring_search_row<MemList, LINEAR>(g, src, cand, self_mode != 0, p, L, evals);
+            ring_search_row<MemList, LINEAR>(g, src, cand, self_mode, p, L, evals);
             amb += list_ambiguous(L, nth_eff) ? 1 : 0;
             for (uint32_t k = 0; k < nth_eff; ++k) {
                 const uint32_t q = L.get_q(k);
@@ -364,7 +367,7 @@ void dispatch_brute(int K, dim3 grid, cudaStream_t s, int sin_model, const doubl
 }  // namespace
 
 int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const CatView& cand,
-                                 bool self, uint32_t nth_eff, uint64_t plane_stride,
+                                 int self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
                                  uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
                                  SearchCounters* ctr, cudaStream_t s, Error& err,
