@@ -49,7 +49,8 @@ int vif_main(int argc, char* argv[]) {
         r = qxmatch(c1, c2, p);                    // catalog overload (qxmatch2.cpp:130)
     }
 
-    id_pair best = xmatch_clean_best(r);           // mutual-best idiom of the callers
+    id_pair best;                                  // mutual-best idiom of the callers (needs rid)
+    if (!p.no_mirror && flags.find('s') == std::string::npos) best = xmatch_clean_best(r);
     f = fopen(argv[2], "wb");
     if (!f) return 4;
     uint_t hdr[6] = {r.id.dims[0], r.id.dims[1], r.rid.size(), r.rd.size(), best.id1.size(), best.lost.size()};

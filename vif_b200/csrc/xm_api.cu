@@ -229,17 +229,48 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
                                            y2.as<double>(), c2.as<double>(), s, err, &launches))) return rc;
             px2 = x2.as<double>(); py2 = y2.as<double>(); pc2 = c2.as<double>();
         }
+        const bool fast = !P.exact_only && brute_fast_applicable(linear, (uint32_t)nth);
+        Scratch u1, u2, rlist, rthr;
+        const void *pu1 = nullptr, *pu2 = nullptr;
+        if (fast) {
+            // unit vectors of both catalogs for the dot-product filter (xm_brute_fast.cu)
+            XM_CUDA_TRY(u1.alloc(brute_uvec_bytes(n1), s));
+            if ((rc = launch_unit_vectors(x1.as<double>(), y1.as<double>(), c1.as<double>(), (uint32_t)n1,
+                                          u1.p, s, err, &launches))) return rc;
+            pu1 = u1.p; pu2 = u1.p;
+            if (!same_cat) {
+                XM_CUDA_TRY(u2.alloc(brute_uvec_bytes(n2), s));
+                if ((rc = launch_unit_vectors(px2, py2, pc2, (uint32_t)n2, u2.p, s, err, &launches))) return rc;
+                pu2 = u2.p;
+            }
+            XM_CUDA_TRY(rlist.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
+            XM_CUDA_TRY(rthr.alloc((size_t)(n1 > n2 ? n1 : n2)*8, s));
+        }
         XM_CUDA_TRY(cudaEventRecord(ev[5], s));
-        if ((rc = launch_brute_exact(g, x1.as<double>(), y1.as<double>(), c1.as<double>(), (uint32_t)n1,
-                                     px2, py2, pc2, (uint32_t)n2, self, (uint32_t)nth, n1, id, d,
-                                     nullptr, (uint32_t)n1, false, ctx->d_ctr, s, err, &launches))) return rc;
+        if (fast) {
+            if ((rc = launch_brute_fast(sin_model, pu1, (uint32_t)n1, pu2, (uint32_t)n2, x1.as<double>(),
+                                        y1.as<double>(), c1.as<double>(), px2, py2, pc2, self, (uint32_t)nth,
+                                        n1, id, d, rlist.as<uint32_t>(), rthr.as<double>(),
+                                        &ctx->d_ctr->refine_fwd, ctx->d_ctr, s, err, &launches))) return rc;
+        } else {
+            if ((rc = launch_brute_exact(g, x1.as<double>(), y1.as<double>(), c1.as<double>(), (uint32_t)n1,
+                                         px2, py2, pc2, (uint32_t)n2, self, (uint32_t)nth, n1, id, d,
+                                         nullptr, (uint32_t)n1, false, ctx->d_ctr, s, err, &launches))) return rc;
+        }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
         if (mirror) {
             // reverse match = the same search with the roles swapped: ascending i, strict '<',
             // i.e. the thread=1 rule (smallest i wins exact ties, qxmatch.hpp:510-513)
-            if ((rc = launch_brute_exact(g, px2, py2, pc2, (uint32_t)n2, x1.as<double>(), y1.as<double>(),
-                                         c1.as<double>(), (uint32_t)n1, self, 1u, n2, rid, rd, nullptr,
-                                         (uint32_t)n2, true, ctx->d_ctr, s, err, &launches))) return rc;
+            if (fast) {
+                if ((rc = launch_brute_fast(sin_model, pu2, (uint32_t)n2, pu1, (uint32_t)n1, px2, py2, pc2,
+                                            x1.as<double>(), y1.as<double>(), c1.as<double>(), self, 1u, n2,
+                                            rid, rd, rlist.as<uint32_t>(), rthr.as<double>(),
+                                            &ctx->d_ctr->refine_rev, ctx->d_ctr, s, err, &launches))) return rc;
+            } else {
+                if ((rc = launch_brute_exact(g, px2, py2, pc2, (uint32_t)n2, x1.as<double>(), y1.as<double>(),
+                                             c1.as<double>(), (uint32_t)n1, self, 1u, n2, rid, rd, nullptr,
+                                             (uint32_t)n2, true, ctx->d_ctr, s, err, &launches))) return rc;
+            }
         }
         XM_CUDA_TRY(cudaEventRecord(ev[7], s));
         XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
@@ -349,6 +380,10 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
     st.ms_total = ev_ms(ev[0], ev[8]);
     st.launches = launches;
     st.evals_fwd = ctx->h_ctr->evals_fwd; st.evals_rev = ctx->h_ctr->evals_rev;
+    if (P.brute_force) {                 // every pair is evaluated once per direction
+        st.evals_fwd = n1*n2 - (self ? (n1 < n2 ? n1 : n2) : 0);
+        st.evals_rev = mirror ? st.evals_fwd : 0;
+    }
     st.rows_ambiguous = ctx->h_ctr->ambiguous;
     st.rows_refined_fwd = ctx->h_ctr->refine_fwd; st.rows_refined_rev = ctx->h_ctr->refine_rev;
     if (P.verbose) {

@@ -112,6 +112,17 @@ int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1
                            uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows,
                            bool reverse, SearchCounters* ctr, cudaStream_t s, Error& err,
                            uint64_t* launches);
+// xm_brute_fast.cu: dot-product filter + exact refine for brute_force (spherical, nth <= 4)
+size_t  brute_uvec_bytes(uint64_t n);
+bool    brute_fast_applicable(bool linear, uint32_t nth);
+int32_t launch_unit_vectors(const double* x, const double* y, const double* c, uint32_t n, void* out,
+                            cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_brute_fast(int sin_model, const void* u1, uint32_t n1, const void* u2, uint32_t n2,
+                          const double* x1, const double* y1, const double* c1, const double* x2,
+                          const double* y2, const double* c2, bool self, uint32_t nth,
+                          uint64_t plane_stride, uint64_t* id_out, double* d_out, uint32_t* refine_list,
+                          double* refine_thr, unsigned long long* refine_count, SearchCounters* ctr,
+                          cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
                              uint64_t* launches);
