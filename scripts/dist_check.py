@@ -1,0 +1,34 @@
+"""Run under torchrun (N ranks, one GPU each): row-sharded qxmatch must equal the single-GPU result
+bit for bit (ids) on the binned and the brute-force paths. Rank 0 prints OK/FAIL lines."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from vif_b200 import qxmatch, catalogs as G
+from vif_b200.qxmatch import QxmatchParams
+from vif_b200.distributed import qxmatch_sharded, shard_bounds
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok_all = True
+for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 100_000, 120_000, dict(nth=3)),
+                         ("brute", 20_000, 15_000, dict(brute_force=True)), ("nomirror", 50_000, 50_000, dict(no_mirror=True))):
+    full1 = G.c2(1, n1, xp="torch", device=dev)
+    full2 = G.c2(2, n2, xp="torch", device=dev)
+    lo, hi = shard_bounds(n1, world, rank)
+    ra2 = full2[0].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    dec2 = full2[1].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    ident, d, rid, rd = qxmatch_sharded(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2, dec2, lo,
+                                        QxmatchParams(device=local, **kw))
+    ref = qxmatch(full1[0], full1[1], full2[0], full2[1], device=local, **kw)
+    ok = torch.equal(ident, ref.id[:, lo:hi]) and torch.equal(d, ref.d[:, lo:hi])
+    if not kw.get("no_mirror"):
+        ok = ok and torch.equal(rid, ref.rid) and torch.equal(rd, ref.rd)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
+    ok_all &= bool(flag.item())
+dist.destroy_process_group()
+sys.exit(0 if ok_all else 1)

@@ -127,7 +127,7 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
                     cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
     Scratch key, perm, tmpk, tmpv, sscr;
     XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
-    XM_CUDA_TRY(out.cell.alloc((size_t)ncell*sizeof(uint2), s));
+    XM_CUDA_TRY(out.cell.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
     XM_CUDA_TRY(key.alloc((size_t)n*4, s));
     XM_CUDA_TRY(perm.alloc((size_t)n*4, s));
     XM_CUDA_TRY(tmpk.alloc((size_t)n*4, s));
@@ -143,10 +143,10 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
     if (rc) return rc;
     if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
     rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
-                                 g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint2>(), s, err,
+                                 g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint32_t>(), s, err,
                                  launches);
     if (rc) return rc;
-    out.view.rec = out.rec.as<Rec>(); out.view.cell = out.cell.as<uint2>(); out.view.n = n;
+    out.view.rec = out.rec.as<Rec>(); out.view.cstart = out.cell.as<uint32_t>(); out.view.n = n;
     return XM_OK;
 }
 

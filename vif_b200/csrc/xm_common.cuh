@@ -24,7 +24,7 @@ struct __align__(32) Rec {
 
 struct CatView {
     const Rec*   rec;       // sources in cell order (stable: ascending row inside a cell)
-    const uint2* cell;      // per cell: [begin, end) in sorted order (0,0 when empty)
+    const uint32_t* cstart; // CSR: cell k holds sorted slots [cstart[k], cstart[k+1]); ncell+1 entries
     uint32_t     n;
 };
 
@@ -81,7 +81,7 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
                     uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
-                                Rec* rec, uint2* cell, cudaStream_t s, Error& err,
+                                Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
                                 uint64_t* launches);
 // xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
 // by sort_scratch_bytes(n)

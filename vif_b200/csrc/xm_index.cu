@@ -1,5 +1,5 @@
-// Cell index construction: bounding box + finiteness, cell keys, CSR cell ranges and the
-// gather of each catalog into cell order (SoA: x = ra [rad], y = dec [rad], c = cos(dec)).
+// Cell index construction: bounding box + finiteness, cell keys, CSR cell offsets and the
+// gather of each catalog into cell order (32-byte records: x = ra [rad], y = dec [rad], c = cos(dec)).
 //
 // Replaces the reference's eight min/max passes (qxmatch.hpp:232-235), the finiteness checks
 // (:146-149), the unit conversion (:170-181) and the vector-of-vectors bucket fill (:270-288).
@@ -86,24 +86,17 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
     vals[i] = i;
 }
 
-// One pass over the sorted keys: cell ranges by boundary detection (no scan needed; the cell
-// table was zeroed, so empty cells read as [0,0)) fused with the gather into cell order and the
-// unit conversion (:174-180).
+// Gather into cell order fused with the unit conversion (:174-180): one 32-byte record per source.
 __global__ void __launch_bounds__(kThreads)
 cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
                     const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
-                    int linear, Rec* __restrict__ rec, uint2* __restrict__ cell) {
+                    int linear, Rec* __restrict__ rec) {
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const uint32_t k = skeys[p];
-    const uint32_t kprev = p > 0 ? skeys[p - 1] : 0xffffffffu;
-    const uint32_t knext = p + 1 < n ? skeys[p + 1] : 0xffffffffu;
-    if (p == 0 || k != kprev) cell[k].x = p;
-    if (p + 1 == n || k != knext) cell[k].y = p + 1;
     const uint32_t i = perm[p];
     const double r = __ldg(ra + i), d = __ldg(dec + i);
     Rec out;
-    out.idx = i; out.key = k;
+    out.idx = i; out.key = skeys[p];
     if (linear) {
         out.x = r; out.y = d; out.c = 1.0;
     } else {
@@ -112,6 +105,22 @@ cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restri
         out.c = cos(out.y);
     }
     rec[p] = out;
+}
+
+// CSR cell offsets: cstart[k] = number of sources whose key is < k (lower bound in the sorted
+// keys), for k = 0..ncell. Monotone over empty cells too, so a run of consecutive cells of one
+// grid column is one contiguous slot range -- what the search kernels stage with bulk copies.
+__global__ void __launch_bounds__(kThreads)
+cell_offsets_kernel(const uint32_t* __restrict__ skeys, uint32_t n, uint32_t ncell,
+                    uint32_t* __restrict__ cstart) {
+    const uint32_t k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k > ncell) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(skeys + mid) < k) lo = mid + 1; else hi = mid;
+    }
+    cstart[k] = lo;
 }
 
 }  // namespace
@@ -139,12 +148,12 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
 
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
-                                Rec* rec, uint2* cell, cudaStream_t s, Error& err,
+                                Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
                                 uint64_t* launches) {
-    XM_CUDA_TRY(cudaMemsetAsync(cell, 0, (size_t)ncell*sizeof(uint2), s));
+    cell_offsets_kernel<<<(ncell + 1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, n, ncell, cstart);
     cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
-                                                                        linear ? 1 : 0, rec, cell);
-    *launches += 1;
+                                                                        linear ? 1 : 0, rec);
+    *launches += 2;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
 }

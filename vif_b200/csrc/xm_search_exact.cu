@@ -165,7 +165,8 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
         for_each_ring_entry(d, g.nra, g.ndec, dedupe, [&](int bx, int by) {
             const int64_t cx = x0 + bx, cy = y0 + by;
             if (cx < 0 || cx >= (int64_t)g.nra || cy < 0 || cy >= (int64_t)g.ndec) return;
-            const uint2 r = cand.cell[(uint64_t)cx*g.ndec + (uint64_t)cy];
+            const uint64_t ck = (uint64_t)cx*g.ndec + (uint64_t)cy;
+            const uint2 r = make_uint2(cand.cstart[ck], cand.cstart[ck + 1]);
             if (r.x == r.y) return;
             if (d > 0 && cell_lower_bound<LINEAR>(g, x1, y1, c1, cx, cy) >= L.kth()) return;
             for (uint32_t q = r.x; q < r.y; ++q) {

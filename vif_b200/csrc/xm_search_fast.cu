@@ -18,10 +18,8 @@
 //     must go on to ring 2 and beyond are flagged as well (the exact kernel walks any depth).
 // Flagged rows are a few per 10^7 on the benchmark catalogs (xm_stats::rows_refined_*).
 //
-// Work shape: one thread per source, sources and candidates in cell order (32-byte records, one
-// LDG.256 each, warp-broadcast through L1 because neighbouring threads sit in the same cells);
-// ring 0 is the own cell, ring 1 the other 24 cells of the 5x5 block, visited nearest-first from a
-// per-thread survivor bitmask so that lanes do not wait on cells only other lanes need.
+// Work shape: see ring_nn_filter_kernel below (one CTA = a strip of one grid column, candidates
+// staged in shared memory by the TMA engine, ring-1 work redistributed over the CTA).
 #include "xm_common.cuh"
 #include "xm_math_exact.cuh"
 
@@ -80,7 +78,7 @@ __device__ __forceinline__ void eval_loaded(const Rec& cd, uint32_t q, double x1
     b.slot = better ? q : b.slot;
 }
 
-// all candidates of one cell; four independent 32-byte loads in flight per step
+// all candidates of one cell read from global memory; four independent 32-byte loads in flight
 template <bool SELF>
 __device__ __forceinline__ void scan_range(const Rec* __restrict__ rec, uint32_t qs, uint32_t qe,
                                            double x1, double y1, double c1, uint32_t self_slot,
@@ -106,8 +104,17 @@ __device__ __forceinline__ void scan_range(const Rec* __restrict__ rec, uint32_t
     }
 }
 
-// 0: stop for certain, 1: continue for certain, 2: inside the slack
-// (q1 is only known to lie in [q1_lo, q1_hi))
+// the same cell read from the CTA's staged copy: slot q lives at stage[q + delta]
+template <bool SELF>
+__device__ __forceinline__ void scan_range_staged(const Rec* stage, int32_t delta, uint32_t qs,
+                                                  uint32_t qe, double x1, double y1, double c1,
+                                                  uint32_t self_slot, Best& b) {
+#pragma unroll 2
+    for (uint32_t q = qs; q < qe; ++q) eval_loaded<SELF>(stage[(int32_t)q + delta], q, x1, y1, c1, self_slot, b);
+}
+
+// Stop rule of qxmatch.hpp:336-340 on the small-angle forms. 0: stop for certain, 1: continue for
+// certain, 2: inside the slack. q1 is only known to lie in [q1_lo, q1_hi).
 __device__ __forceinline__ int stop_decision(double q1_lo, double q1_hi, double tr, const GridView& g) {
     const double lo = tr - g.stop_delta, hi = tr + g.stop_delta;
     if (lo > 0.0 && q1_hi*(1.0 + g.eps_hi) <= lo*lo*(1.0 - lo*lo*(1.0/12.0) - 1e-12)) return 0;
@@ -125,35 +132,124 @@ __device__ __forceinline__ void merge_best(Best& b, int32_t a1, int32_t a2, uint
 }
 
 constexpr int kMaxItems = 4*kThreads;    // ring-1 work items a CTA can queue (4 per source; typical total ~90)
+constexpr int kStageCap = 768;           // candidate records a CTA can stage (24 KB; typical need ~450)
+constexpr int kStageRows = 40;           // cell rows (incl. halo) a staged block may span
+constexpr int32_t kNotStaged = INT32_MIN;
 
-// Work shape of one CTA (128 consecutive sources in cell order):
+// ---- TMA bulk copy (1-D, no tensor map) + mbarrier ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Work shape of one CTA (128 consecutive sources in cell order = a short strip of one grid column):
+//   0. the candidate records of the strip's 3-column neighbourhood (rows +-1) are contiguous slot
+//      runs of the cell-ordered catalog (one per column): the TMA engine copies them into shared
+//      memory (cp.async.bulk + mbarrier) together with their CSR offsets; strips that straddle two
+//      columns or overflow the stage read global memory instead (same code path otherwise);
 //   1. every thread scans its source's own cell (ring 0), applies the stop rule and derives the
 //      bitmask of ring-1 cells that survive the culling test;
-//   2. the surviving (source, cell) pairs are queued in shared memory (block-wide prefix sum), so
-//      that
+//   2. the surviving non-empty (source, cell) pairs are queued in shared memory (block prefix sum);
 //   3. the CTA's threads take one queued pair each -- a source that needs three neighbouring cells
 //      no longer stalls the 31 lanes next to it that need none;
 //   4. every thread merges the partial results of its own source, applies the stop rule of ring 1
 //      and the ambiguity test, and writes id / d (or queues the row for the exact kernel).
 template <bool SELF>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads)
 ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restrict__ id_out,
                       double* __restrict__ d_out, uint32_t* __restrict__ refine_list,
                       unsigned long long* refine_count, int reverse, SearchCounters* ctr) {
+    __shared__ __align__(128) Rec s_cand[kStageCap];
+    __shared__ uint32_t s_cs[3][kStageRows + 1];        // CSR offsets of the staged block, per column
+    __shared__ int32_t  s_delta[3];                     // slot -> stage index shift, per column
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_klast;
+    __shared__ int      s_staged;
     __shared__ double s_x[kThreads], s_y[kThreads], s_c[kThreads];
     __shared__ uint8_t  s_owner[kMaxItems];             // thread that owns the queued (source, cell) pair
     __shared__ uint2    s_range[kMaxItems];             // candidate slots of the cell
+    __shared__ int32_t  s_shift[kMaxItems];             // stage shift of the cell, kNotStaged = global
     __shared__ int32_t  s_a1[kMaxItems], s_a2[kMaxItems];
     __shared__ uint32_t s_slot[kMaxItems];
     __shared__ uint32_t s_warp_tot[kThreads/32];
 
-    const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    const uint32_t p0 = blockIdx.x*blockDim.x;
+    const uint32_t p = p0 + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool live = p < src.n;
+    const int ndec = (int)g.ndec, nra = (int)g.nra;
     uint32_t evals = 0;
 
     Rec me;
     me.x = me.y = me.c = 0.0; me.idx = 0; me.key = 0;
+    if (live) me = load_rec(src.rec + p);
+    const uint32_t nlive = min((uint32_t)kThreads, src.n - p0);
+    if (threadIdx.x == nlive - 1) s_klast = me.key;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first key of the strip: thread 0's
+    const uint32_t kfirst = __shfl_sync(0xffffffffu, me.key, 0);
+    __shared__ uint32_t s_kfirst;
+    if (threadIdx.x == 0) s_kfirst = kfirst;
+    __syncthreads();
+
+    // ---- 0. stage the neighbourhood -------------------------------------------------------------------
+    const uint32_t kf = s_kfirst, kl = s_klast;
+    const int xs = (int)(kf/g.ndec), yf = (int)(kf - (uint32_t)xs*g.ndec);
+    const int xl = (int)(kl/g.ndec), yl = (int)(kl - (uint32_t)xl*g.ndec);
+    const int ya = max(yf - 1, 0), yb = min(yl + 1, ndec - 1);
+    const int nrows = yb - ya + 1;
+    const bool try_stage = (xs == xl) && nrows <= kStageRows;
+    if (try_stage) {
+        for (int t = threadIdx.x; t < 3*(nrows + 1); t += kThreads) {
+            const int col = t/(nrows + 1), r = t - col*(nrows + 1);
+            const int cx = xs - 1 + col;
+            s_cs[col][r] = (cx >= 0 && cx < nra) ? cand.cstart[(uint32_t)cx*g.ndec + (uint32_t)(ya + r)] : 0u;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int staged = 0;
+        if (try_stage) {
+            uint32_t tot = 0;
+            for (int col = 0; col < 3; ++col) tot += s_cs[col][nrows] - s_cs[col][0];
+            if (tot <= (uint32_t)kStageCap) {
+                staged = 1;
+                uint32_t off = 0;
+                if (tot) mbar_expect_tx(&s_bar, tot*(uint32_t)sizeof(Rec));
+                for (int col = 0; col < 3; ++col) {
+                    const uint32_t b0 = s_cs[col][0], cnt = s_cs[col][nrows] - b0;
+                    s_delta[col] = (int32_t)off - (int32_t)b0;
+                    if (cnt) bulk_g2s(&s_cand[off], cand.rec + b0, cnt*(uint32_t)sizeof(Rec), &s_bar);
+                    off += cnt;
+                }
+                if (!tot) staged = 2;                   // nothing to wait for
+            }
+        }
+        s_staged = staged;
+    }
+    __syncthreads();
+    const int staged = s_staged;
+    if (staged == 1) mbar_wait(&s_bar, 0);
+
     Best b;
     b.h1 = kInfHi; b.h2 = kInfHi; b.slot = 0xffffffffu;
     bool flag = false, done = !live;
@@ -162,14 +258,17 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
     double cdist = 0.0;
 
     if (live) {
-        me = load_rec(src.rec + p);
         x0 = (int)(me.key/g.ndec); y0 = (int)(me.key - (uint32_t)x0*g.ndec);
         const double x1 = me.x, y1 = me.y, c1 = me.c;
-        // ---- ring 0: own cell ------------------------------------------------------------------
-        {
-            const uint2 r = cand.cell[me.key];
-            scan_range<SELF>(cand.rec, r.x, r.y, x1, y1, c1, p, b);
-            evals += r.y - r.x;
+        // ---- 1. ring 0: own cell ---------------------------------------------------------------------
+        if (staged) {
+            const uint32_t qs = s_cs[1][y0 - ya], qe = s_cs[1][y0 - ya + 1];
+            scan_range_staged<SELF>(s_cand, s_delta[1], qs, qe, x1, y1, c1, p, b);
+            evals += qe - qs;
+        } else {
+            const uint32_t qs = cand.cstart[me.key], qe = cand.cstart[me.key + 1];
+            scan_range<SELF>(cand.rec, qs, qe, x1, y1, c1, p, b);
+            evals += qe - qs;
         }
         // distance to the cell centre and the stop rule after ring 0 (max_dist = cs/2)
         const double ex_lo = g.ox + (double)x0*g.wx, ey_lo = g.oy + (double)y0*g.wy;
@@ -181,7 +280,6 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
         }
         if (!done) {
             // ---- ring 1: which of the other 24 cells of the 5x5 block can hold a winner? ---------
-            const int ndec = (int)g.ndec, nra = (int)g.nra;
             double gl = x1 - ex_lo - g.fzx, gr = (ex_lo + g.wx) - x1 - g.fzx;
             double gd = y1 - ey_lo - g.fzy, gu = (ey_lo + g.wy) - y1 - g.fzy;
             gl = gl > 0 ? gl : 0; gr = gr > 0 ? gr : 0; gd = gd > 0 ? gd : 0; gu = gu > 0 ? gu : 0;
@@ -212,28 +310,39 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
         }
     }
 
-    // ---- queue the surviving (source, cell) pairs ------------------------------------------------
-    // The owner fetches the cells' candidate ranges itself (independent loads, issued back to back)
-    // and queues only non-empty cells, so the thread that later takes a pair starts on the
-    // candidates right away.
+    // ---- 2. queue the surviving (source, cell) pairs ---------------------------------------------------
+    // The owner resolves each cell's slot range (from the staged CSR offsets when the cell is inside
+    // the staged block) and queues only non-empty cells.
     s_x[threadIdx.x] = me.x; s_y[threadIdx.x] = me.y; s_c[threadIdx.x] = me.c;
     uint2 rng[4];
+    int32_t shf[4];
     uint32_t cnt = 0;
-    bool spill = false;                                 // more than 4 non-empty cells: scan in place
     {
         uint32_t m = mask;
         while (m) {
             const int e = __ffs(m) - 1;
             m &= m - 1;
-            const uint2 r = cand.cell[(uint32_t)((int)me.key + (int)c_bx[e]*(int)g.ndec + (int)c_by[e])];
+            const int bx = c_bx[e], by = c_by[e];
+            const int ry = y0 + by - ya;
+            uint2 r; int32_t sh;
+            if (staged && bx >= -1 && bx <= 1 && ry >= 0 && ry < nrows) {
+                r = make_uint2(s_cs[bx + 1][ry], s_cs[bx + 1][ry + 1]);
+                sh = s_delta[bx + 1];
+            } else {
+                const uint32_t ck = (uint32_t)((int)me.key + bx*ndec + by);
+                r = make_uint2(cand.cstart[ck], cand.cstart[ck + 1]);
+                sh = kNotStaged;
+            }
             if (r.x == r.y) continue;
             if (cnt < 4) {
-                // static indexing keeps rng[] in registers
-                if (cnt == 0) rng[0] = r; else if (cnt == 1) rng[1] = r; else if (cnt == 2) rng[2] = r; else rng[3] = r;
+                // static indexing keeps rng[] / shf[] in registers
+                if (cnt == 0) { rng[0] = r; shf[0] = sh; } else if (cnt == 1) { rng[1] = r; shf[1] = sh; }
+                else if (cnt == 2) { rng[2] = r; shf[2] = sh; } else { rng[3] = r; shf[3] = sh; }
                 ++cnt;
             } else {
-                spill = true;
-                scan_range<SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, p, b);
+                // more than 4 non-empty cells for one source: scan the rest in place
+                if (sh != kNotStaged) scan_range_staged<SELF>(s_cand, sh, r.x, r.y, me.x, me.y, me.c, p, b);
+                else scan_range<SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, p, b);
                 evals += r.y - r.x;
             }
         }
@@ -252,28 +361,31 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
         if (k < wid) first += s_warp_tot[k];
         total += s_warp_tot[k];
     }
-    // total <= 4*kThreads <= kMaxItems by construction
+    // total <= 4*kThreads = kMaxItems by construction
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if ((uint32_t)k < cnt) { s_owner[first + k] = (uint8_t)threadIdx.x; s_range[first + k] = rng[k]; }
+        if ((uint32_t)k < cnt) {
+            s_owner[first + k] = (uint8_t)threadIdx.x; s_range[first + k] = rng[k]; s_shift[first + k] = shf[k];
+        }
     }
     __syncthreads();
 
-    // ---- one queued pair per thread ----------------------------------------------------------------
+    // ---- 3. one queued pair per thread ------------------------------------------------------------------
     for (uint32_t it = threadIdx.x; it < total; it += kThreads) {
         const int owner = s_owner[it];
         const uint2 r = s_range[it];
+        const int32_t sh = s_shift[it];
         Best a;
         a.h1 = kInfHi; a.h2 = kInfHi; a.slot = 0xffffffffu;
-        scan_range<SELF>(cand.rec, r.x, r.y, s_x[owner], s_y[owner], s_c[owner],
-                         blockIdx.x*blockDim.x + owner, a);
+        if (sh != kNotStaged) scan_range_staged<SELF>(s_cand, sh, r.x, r.y, s_x[owner], s_y[owner], s_c[owner], p0 + owner, a);
+        else scan_range<SELF>(cand.rec, r.x, r.y, s_x[owner], s_y[owner], s_c[owner], p0 + owner, a);
         evals += r.y - r.x;
         s_a1[it] = a.h1; s_a2[it] = a.h2; s_slot[it] = a.slot;
     }
     __syncthreads();
     for (uint32_t k = 0; k < cnt; ++k) merge_best(b, s_a1[first + k], s_a2[first + k], s_slot[first + k]);
-    (void)spill;
 
+    // ---- 4. decide ----------------------------------------------------------------------------------------
     if (live) {
         if (!done) {
             // stop rule after ring 1 (max_dist = 2.5 cs): going on to ring 2 is the exact kernel's job
