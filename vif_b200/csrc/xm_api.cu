@@ -335,10 +335,13 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
         // the rows it flags (list length stays on the device: no host round trip)
         const bool fast = !P.exact_only && fast_path_applicable(g) && self_mode != 2;
-        Scratch refine;
-        if (fast) XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
+        Scratch refine, resrec;
+        if (fast) {
+            XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
+            XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1 > n2 ? n1 : n2), s));
+        }
         if (fast && nth_eff == 1) {
-            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, refine.as<uint32_t>(),
+            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
             if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
                                                (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s,
@@ -351,7 +354,7 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         if (mirror) {
             if (!self) {
                 if (fast) {
-                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, refine.as<uint32_t>(),
+                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec.p, refine.as<uint32_t>(),
                                                     &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
                                                        refine.as<uint32_t>(), (uint32_t)n2,

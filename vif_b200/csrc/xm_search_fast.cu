@@ -52,6 +52,13 @@ __device__ __forceinline__ Rec load_rec(const Rec* p) {
 // native 32-bit integer min/max (FP64 min/max are multi-instruction selects on sm_100) and the slot
 // of the smallest. Two metrics with different high words are strictly ordered; metrics sharing a
 // high word (within 2^-20 of each other) are told apart by the exact kernel.
+// result of one source, padded to a DRAM sector; unpack_results_kernel splits it into id[] / d[]
+struct __align__(32) ResRec { uint64_t id; double d; uint64_t pad0, pad1; };
+
+__device__ __forceinline__ void store_res(ResRec* p, uint64_t id, double d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%3};" :: "l"(p), "l"(id), "l"(__double_as_longlong(d)), "l"(0ll) : "memory");
+}
+
 struct Best {
     int32_t h1, h2;
     uint32_t slot;
@@ -174,9 +181,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 //      and the ambiguity test, and writes id / d (or queues the row for the exact kernel).
 template <bool SELF>
 __global__ void __launch_bounds__(kThreads)
-ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restrict__ id_out,
-                      double* __restrict__ d_out, uint32_t* __restrict__ refine_list,
-                      unsigned long long* refine_count, int reverse, SearchCounters* ctr) {
+ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict__ res,
+                      uint32_t* __restrict__ refine_list, unsigned long long* refine_count,
+                      int reverse, SearchCounters* ctr) {
     __shared__ __align__(128) Rec s_cand[kStageCap];
     __shared__ uint32_t s_cs[3][kStageRows + 1];        // CSR offsets of the staged block, per column
     __shared__ int32_t  s_delta[3];                     // slot -> stage index shift, per column
@@ -258,7 +265,8 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
     double cdist = 0.0;
 
     if (live) {
-        x0 = (int)(me.key/g.ndec); y0 = (int)(me.key - (uint32_t)x0*g.ndec);
+        if (xs == xl) x0 = xs; else x0 = (int)(me.key/g.ndec);     // one-column strips skip the division
+        y0 = (int)(me.key - (uint32_t)x0*g.ndec);
         const double x1 = me.x, y1 = me.y, c1 = me.c;
         // ---- 1. ring 0: own cell ---------------------------------------------------------------------
         if (staged) {
@@ -295,12 +303,17 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
                 CM[k] = (yy >= 0 && yy < ndec) ? g.cmin_row[yy]*shrink : -1.0;
             }
             const double thr = hi_ceil(b.h1)*(1.0 + g.eps_hi)*(1.0 + 1e-9);
+            // the 16 outer cells lie at least one full cell away: one test rules them all out for
+            // most sources (min over the four directions of the bound of the nearest outer cell)
+            const double cm_lo = fmin(fmin(CM[0], CM[1]), fmin(fmin(CM[2], CM[3]), CM[4]));
+            const bool outer = !(fmin(fmin(GX[0], GX[4])*fmax(cm_lo, 0.0), fmin(GY[0], GY[4])) >= thr) || cm_lo < 0.0;
 #pragma unroll
             for (int e = 0; e < 24; ++e) {
                 constexpr int8_t BX[24] = {0, 1, 0, -1, 1, -1, -1, 1,
                                            0, 1, 2, 2, 2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1};
                 constexpr int8_t BY[24] = {1, 0, -1, 0, 1, 1, -1, -1,
                                            2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1, 0, 1, 2, 2};
+                if (e == 8 && !outer) break;
                 const int bx = BX[e], by = BY[e];
                 const int cx = x0 + bx;
                 const double cm = CM[by + 2];
@@ -404,8 +417,9 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
             // exact proxy of the winning pair in reference-order arithmetic -> arcsec
             const Rec w = load_rec(cand.rec + b.slot);
             const double pr = proxy_sph_small(me.x, me.y, me.c, w.x, w.y, w.c, g.sin_model);
-            id_out[me.idx] = (uint64_t)w.idx;
-            d_out[me.idx] = proxy_to_true(pr, false);
+            // one full 32-byte sector per source at its original row: a scattered 8-byte store would
+            // cost a sector read-modify-write in DRAM for each of id and d
+            store_res(res + me.idx, (uint64_t)w.idx, proxy_to_true_small(pr));
         }
     }
     unsigned long long v = evals;
@@ -413,7 +427,20 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, uint64_t* __restric
     if (lane == 0 && v) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, v);
 }
 
+__global__ void __launch_bounds__(256)
+unpack_results_kernel(const ResRec* __restrict__ res, uint32_t n, uint64_t* __restrict__ id_out,
+                      double* __restrict__ d_out) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(res + i));
+    id_out[i] = a;
+    d_out[i] = __longlong_as_double((long long)b);
+}
+
 }  // namespace
+
+size_t filter_result_bytes(uint64_t n) { return (size_t)n*sizeof(ResRec); }
 
 // The filter's bounds assume small cells well away from the poles; everything else is the exact
 // kernel's job.
@@ -427,16 +454,19 @@ bool fast_path_applicable(const GridView& g) {
 }
 
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
-                              uint64_t* id_out, double* d_out, uint32_t* refine_list,
-                              unsigned long long* refine_count, bool reverse, SearchCounters* ctr,
-                              cudaStream_t s, Error& err, uint64_t* launches) {
+                              uint64_t* id_out, double* d_out, void* result_scratch,
+                              uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
+                              SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches) {
     if (src.n == 0) return XM_OK;
     const dim3 grid((src.n + kThreads - 1)/kThreads);
-    if (self) ring_nn_filter_kernel<true><<<grid, kThreads, 0, s>>>(g, src, cand, id_out, d_out, refine_list,
+    ResRec* res = (ResRec*)result_scratch;
+    if (self) ring_nn_filter_kernel<true><<<grid, kThreads, 0, s>>>(g, src, cand, res, refine_list,
                                                                    refine_count, reverse ? 1 : 0, ctr);
-    else ring_nn_filter_kernel<false><<<grid, kThreads, 0, s>>>(g, src, cand, id_out, d_out, refine_list,
+    else ring_nn_filter_kernel<false><<<grid, kThreads, 0, s>>>(g, src, cand, res, refine_list,
                                                                 refine_count, reverse ? 1 : 0, ctr);
-    *launches += 1;
+    // rows flagged for the exact kernel carry garbage here; it overwrites them afterwards
+    unpack_results_kernel<<<(src.n + 255)/256, 256, 0, s>>>(res, src.n, id_out, d_out);
+    *launches += 2;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
 }
