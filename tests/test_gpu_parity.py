@@ -98,6 +98,33 @@ def test_self_with_distinct_arrays(oracle):
     assert np.array_equal(got1.id[0], exp["id"][0])
 
 
+def test_bucket_and_radix_index_agree(monkeypatch):
+    """The counting-sort index (default) and the stable radix-sort index must give identical bits."""
+    ra1, dec1 = G.c1(31, 80_000); ra2, dec2 = G.c1(32, 70_000)
+    for kw in (dict(), dict(nth=3), dict(nth=4, self=True)):
+        same = kw.pop("self", False)
+        a = qxmatch(ra1, dec1, None if same else ra2, None if same else dec2, **kw)
+        monkeypatch.setenv("XM_INDEX", "radix")
+        b = qxmatch(ra1, dec1, None if same else ra2, None if same else dec2, **kw)
+        monkeypatch.delenv("XM_INDEX")
+        for k in ("id", "rid"):
+            assert np.array_equal(getattr(a, k), getattr(b, k))
+        for k in ("d", "rd"):
+            assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True)
+        assert a.stats["launches"] != b.stats["launches"]      # two different pipelines did run
+
+
+def test_crowded_cell_falls_back_to_radix_index(oracle):
+    """> 4096 sources in one cell: the bucket index reports an overflow, the call is redone with
+    the radix-sort index; results still match the oracle (exact ties resolved by row order)."""
+    ra2, dec2 = G.c1(33, 30_000)
+    ra2[:6000] = 0.5; dec2[:6000] = 0.5                    # 6000 identical points -> one cell
+    ra1, dec1 = G.c1(34, 5_000)
+    exp = oracle.oracle_qxmatch(ra1, dec1, ra2, dec2, thread=8, nth=2)
+    got = qxmatch(ra1, dec1, ra2, dec2, nth=2)
+    assert_same_result(got, exp, RTOL, "crowded")
+
+
 def test_errors_nonfinite_and_grid():
     a = np.array([0.1, np.nan, 0.3]); b = np.array([0.1, 0.2, 0.3])
     with pytest.raises(QxmatchError, match="first RA and Dec coordinates contain invalid values"):

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -121,31 +122,45 @@ struct SortedCat {
     CatView view{};
 };
 
-// keys -> sort -> cell ranges + gather (one catalog)
+// One catalog -> cell-ordered records + CSR offsets. use_bucket: counting-sort placement
+// (xm_bucket.cu); otherwise keys -> stable radix sort -> gather (no limit on cell occupancy).
 int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
-                    uint32_t ncell, SortedCat& out, cudaStream_t s, Error& err, uint64_t* launches,
-                    cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
-    Scratch key, perm, tmpk, tmpv, sscr;
+                    uint32_t ncell, bool use_bucket, uint32_t* overflow, SortedCat& out, cudaStream_t s,
+                    Error& err, uint64_t* launches, cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
     XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
     XM_CUDA_TRY(out.cell.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
-    XM_CUDA_TRY(key.alloc((size_t)n*4, s));
-    XM_CUDA_TRY(perm.alloc((size_t)n*4, s));
-    XM_CUDA_TRY(tmpk.alloc((size_t)n*4, s));
-    XM_CUDA_TRY(tmpv.alloc((size_t)n*4, s));
-    XM_CUDA_TRY(sscr.alloc(sort_scratch_bytes(n), s));
-    int32_t rc = launch_keys(ra, dec, n, g, key.as<uint32_t>(), perm.as<uint32_t>(), s, err, launches);
-    if (rc) return rc;
-    if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
-    int bits = 1;
-    while (bits < 32 && (1ull << bits) < (uint64_t)ncell) ++bits;
-    rc = launch_sort_pairs(key.as<uint32_t>(), perm.as<uint32_t>(), tmpk.as<uint32_t>(),
-                           tmpv.as<uint32_t>(), n, bits, sscr.p, s, err, launches);
-    if (rc) return rc;
-    if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
-    rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
-                                 g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint32_t>(), s, err,
-                                 launches);
-    if (rc) return rc;
+    int32_t rc;
+    if (use_bucket) {
+        Scratch tmp, cursor, aux;
+        XM_CUDA_TRY(tmp.alloc((size_t)n*sizeof(Rec), s));
+        XM_CUDA_TRY(cursor.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
+        XM_CUDA_TRY(aux.alloc(bucket_scan_aux_bytes(ncell), s));
+        rc = launch_bucket_index(ra, dec, n, g, ncell, tmp.as<Rec>(), out.rec.as<Rec>(), out.cell.as<uint32_t>(),
+                                 cursor.as<uint32_t>(), aux.as<uint32_t>(), overflow, s, err, launches);
+        if (rc) return rc;
+        if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
+        if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
+    } else {
+        Scratch key, perm, tmpk, tmpv, sscr;
+        XM_CUDA_TRY(key.alloc((size_t)n*4, s));
+        XM_CUDA_TRY(perm.alloc((size_t)n*4, s));
+        XM_CUDA_TRY(tmpk.alloc((size_t)n*4, s));
+        XM_CUDA_TRY(tmpv.alloc((size_t)n*4, s));
+        XM_CUDA_TRY(sscr.alloc(sort_scratch_bytes(n), s));
+        rc = launch_keys(ra, dec, n, g, key.as<uint32_t>(), perm.as<uint32_t>(), s, err, launches);
+        if (rc) return rc;
+        if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (uint64_t)ncell) ++bits;
+        rc = launch_sort_pairs(key.as<uint32_t>(), perm.as<uint32_t>(), tmpk.as<uint32_t>(),
+                               tmpv.as<uint32_t>(), n, bits, sscr.p, s, err, launches);
+        if (rc) return rc;
+        if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
+        rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
+                                     g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint32_t>(), s, err,
+                                     launches);
+        if (rc) return rc;
+    }
     out.view.rec = out.rec.as<Rec>(); out.view.cstart = out.cell.as<uint32_t>(); out.view.n = n;
     return XM_OK;
 }
@@ -156,9 +171,9 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
-int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
-                   const double* ra2, const double* dec2, uint64_t n2, const xm_params& P,
-                   uint64_t* id, double* d, uint64_t* rid, double* rd, Error& err) {
+int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
+                        const double* ra2, const double* dec2, uint64_t n2, const xm_params& P,
+                        uint64_t* id, double* d, uint64_t* rid, double* rd, bool use_bucket, Error& err) {
     const uint64_t nth = P.nth < 1 ? 1 : P.nth;
     const bool mirror = !P.no_mirror;
     const bool linear = P.linear != 0;
@@ -316,10 +331,12 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         if (!linear && (rc = launch_row_tables(g, cmin.as<double>(), ccen.as<double>(), s, err, &launches))) return rc;
 
         SortedCat s1, s2;
-        if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, s1, s, err, &launches, ev[2], ev[3]))) return rc;
+        if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, use_bucket, &ctx->d_ctr->index_overflow, s1, s,
+                              err, &launches, ev[2], ev[3]))) return rc;
         const CatView* v2 = &s1.view;
         if (!same_cat) {
-            if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, s2, s, err, &launches, nullptr, nullptr))) return rc;
+            if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, use_bucket, &ctx->d_ctr->index_overflow, s2,
+                                  s, err, &launches, nullptr, nullptr))) return rc;
             v2 = &s2.view;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[5], s));
@@ -397,6 +414,24 @@ int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double
         fflush(stdout);
     }
     return XM_OK;
+}
+
+// The bucket index orders each cell with a bounded in-cell sort; a catalog with a pathologically
+// crowded cell (> 4096 sources) reports an overflow and the call is redone with the radix-sort
+// index, which has no such bound. XM_INDEX=radix forces the latter (tests).
+int32_t run_device(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
+                   const double* ra2, const double* dec2, uint64_t n2, const xm_params& P,
+                   uint64_t* id, double* d, uint64_t* rid, double* rd, Error& err) {
+    const char* env = getenv("XM_INDEX");
+    const bool want_bucket = !(env && strcmp(env, "radix") == 0);
+    ctx->h_ctr->index_overflow = 0;
+    int32_t rc = run_device_once(ctx, s, ra1, dec1, n1, ra2, dec2, n2, P, id, d, rid, rd, want_bucket, err);
+    if (rc == XM_OK && want_bucket && ctx->h_ctr->index_overflow != 0) {
+        const double ms_first = ctx->last.ms_total;
+        rc = run_device_once(ctx, s, ra1, dec1, n1, ra2, dec2, n2, P, id, d, rid, rd, false, err);
+        ctx->last.ms_total += ms_first;
+    }
+    return rc;
 }
 
 void copy_err(const Error& err, char* errbuf, uint64_t errcap) {

@@ -1,0 +1,175 @@
+// Cell index by direct bucket placement -- the fast path of the "bucket fill" (qxmatch.hpp:270-288).
+//
+// The reference pushes row ids into per-cell vectors in ascending row order. Rebuilt here as a
+// counting sort whose every pass streams (no random 8-byte gathers, only full-sector scatters):
+//   1. count:  one pass over (ra, dec): cell key (IEEE subtract/divide/floor as the reference),
+//              atomicAdd on the per-cell counter (the table is L2-resident);
+//   2. scan:   exclusive prefix sum of the counters -> CSR offsets cstart[ncell+1];
+//   3. place:  second pass over (ra, dec): slot = cstart[key] + atomicAdd(cursor[key], 1); the
+//              source's 32-byte record (radians, cos(dec), row, key) is written to that slot -- a
+//              scattered store of one full DRAM sector, no read-modify-write;
+//   4. order:  atomics fill a cell in arbitrary order, the reference's order inside a cell is
+//              ascending row (it decides exact ties): one warp per cell ranks the cell's records by
+//              row and writes them to their final slots (out of place, both sides streamed).
+// Cells holding more than kMaxCellSort rows are left unordered and reported through *overflow; the
+// caller then rebuilds that catalog with the stable radix sort (xm_sort.cu), which has no such limit.
+#include "xm_common.cuh"
+
+namespace xm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kMaxCellSort = 4096;
+
+__device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridView& g) {
+    // qxmatch.hpp:278-279
+    const double fx = floor(__ddiv_rn(__dsub_rn(ra, g.rra0), g.dra));
+    const double fy = floor(__ddiv_rn(__dsub_rn(dec, g.rdec0), g.ddec));
+    const uint32_t ix = fx < 0 ? 0u : (fx >= (double)g.nra ? g.nra - 1 : (uint32_t)fx);
+    const uint32_t iy = fy < 0 ? 0u : (fy >= (double)g.ndec ? g.ndec - 1 : (uint32_t)fy);
+    return ix*g.ndec + iy;
+}
+
+__global__ void __launch_bounds__(kThreads)
+count_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+             uint32_t* __restrict__ count) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(count + cell_key(__ldg(ra + i), __ldg(dec + i), g), 1u);
+}
+
+// ---- exclusive scan of u32 (three-level, in place) ------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads*kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kScanThreads/32; ++k) { if (k < w) off += warp_sums[k]; tot += warp_sums[k]; }
+    total = tot;
+    __syncthreads();
+    return off + inc - v;
+}
+
+// each CTA scans its tile locally and emits the tile total
+__global__ void __launch_bounds__(kScanThreads)
+scan_tiles_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t ws[kScanThreads/32];
+    const uint32_t base = blockIdx.x*kScanTile + threadIdx.x*kScanItems;
+    uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < n ? data[base + k] : 0u; sum += v[k]; }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, ws, total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { if (base + k < n) data[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_add_kernel(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ tile_offs) {
+    const uint32_t off = tile_offs[blockIdx.x];
+    const uint32_t base = blockIdx.x*kScanTile + threadIdx.x*kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) if (base + k < n) data[base + k] += off;
+}
+
+// in-place exclusive scan of data[0..n); aux must hold ceil(n/tile) + ceil(n/tile^2) + 2 words
+void exclusive_scan(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches) {
+    const uint32_t t1 = (n + kScanTile - 1)/kScanTile;
+    scan_tiles_kernel<<<t1, kScanThreads, 0, s>>>(data, n, aux);
+    *launches += 1;
+    if (t1 > 1) {
+        exclusive_scan(aux, t1, aux + t1, s, launches);
+        scan_add_kernel<<<t1, kScanThreads, 0, s>>>(data, n, aux);
+        *launches += 1;
+    }
+}
+
+// ---- placement --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+             const uint32_t* __restrict__ cstart, uint32_t* __restrict__ cursor, Rec* __restrict__ out) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double r = __ldg(ra + i), d = __ldg(dec + i);
+    const uint32_t key = cell_key(r, d, g);
+    const uint32_t slot = cstart[key] + atomicAdd(cursor + key, 1u);
+    double x, y, c;
+    if (g.linear) { x = r; y = d; c = 1.0; }
+    else { y = __dmul_rn(d, XM_D2R); x = __dmul_rn(r, XM_D2R); c = cos(y); }     // qxmatch.hpp:174-180
+    const unsigned long long w = (unsigned long long)i | ((unsigned long long)key << 32);
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(out + slot), "l"(__double_as_longlong(x)),
+                 "l"(__double_as_longlong(y)), "l"(__double_as_longlong(c)), "l"(w) : "memory");
+}
+
+// one warp per cell: rank the cell's records by original row, write them to their final slots
+__global__ void __launch_bounds__(kThreads)
+order_cells_kernel(const Rec* __restrict__ in, const uint32_t* __restrict__ cstart, uint32_t ncell,
+                   Rec* __restrict__ out, uint32_t* __restrict__ overflow) {
+    const uint32_t warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= ncell) return;
+    const uint32_t s = cstart[warp], m = cstart[warp + 1] - s;
+    if (m == 0) return;
+    if (m <= 32) {
+        Rec r;
+        r.x = r.y = r.c = 0.0; r.idx = 0xffffffffu; r.key = 0;
+        if ((uint32_t)lane < m) r = in[s + lane];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < m; ++j) rank += __shfl_sync(0xffffffffu, r.idx, (int)j) < r.idx ? 1u : 0u;
+        if ((uint32_t)lane < m) out[s + rank] = r;
+    } else if (m <= kMaxCellSort) {
+        for (uint32_t e = lane; e < m; e += 32) {
+            const Rec r = in[s + e];
+            uint32_t rank = 0;
+            for (uint32_t f = 0; f < m; ++f) rank += in[s + f].idx < r.idx ? 1u : 0u;
+            out[s + rank] = r;
+        }
+    } else {
+        for (uint32_t e = lane; e < m; e += 32) out[s + e] = in[s + e];
+        if (lane == 0) atomicAdd(overflow, 1u);
+    }
+}
+
+}  // namespace
+
+size_t bucket_scan_aux_bytes(uint32_t ncell) {
+    uint64_t n = (uint64_t)ncell + 1, tot = 4;
+    while (n > 1) { n = (n + kScanTile - 1)/kScanTile; tot += n + 1; }
+    return (size_t)tot*sizeof(uint32_t);
+}
+
+// rec_tmp, rec_out: n records each; cstart, cursor: ncell+1 words; aux: bucket_scan_aux_bytes(ncell);
+// *overflow (device word) is incremented when a cell was too large to order.
+int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
+                            uint32_t ncell, Rec* rec_tmp, Rec* rec_out, uint32_t* cstart,
+                            uint32_t* cursor, uint32_t* aux, uint32_t* overflow, cudaStream_t s,
+                            Error& err, uint64_t* launches) {
+    XM_CUDA_TRY(cudaMemsetAsync(cstart, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
+    XM_CUDA_TRY(cudaMemsetAsync(cursor, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
+    const uint32_t blocks = (n + kThreads - 1)/kThreads;
+    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart);
+    *launches += 1;
+    exclusive_scan(cstart, ncell + 1, aux, s, launches);
+    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, cursor, rec_tmp);
+    const uint64_t threads = (uint64_t)ncell*32;
+    order_cells_kernel<<<(unsigned)((threads + kThreads - 1)/kThreads), kThreads, 0, s>>>(rec_tmp, cstart, ncell,
+                                                                                        rec_out, overflow);
+    *launches += 2;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+}  // namespace xm

@@ -49,6 +49,8 @@ struct GridView {
 
 struct SearchCounters {       // device counters, zeroed per call
     unsigned long long evals_fwd, evals_rev, ambiguous, refine_fwd, refine_rev;
+    unsigned int index_overflow;  // cells too large for the bucket index's in-cell ordering
+    unsigned int pad;
 };
 
 // ---- error plumbing ------------------------------------------------------------------------
@@ -83,6 +85,12 @@ int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, con
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
                                 Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
                                 uint64_t* launches);
+// xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
+size_t  bucket_scan_aux_bytes(uint32_t ncell);
+int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
+                            uint32_t ncell, Rec* rec_tmp, Rec* rec_out, uint32_t* cstart,
+                            uint32_t* cursor, uint32_t* aux, uint32_t* overflow, cudaStream_t s,
+                            Error& err, uint64_t* launches);
 // xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
 // by sort_scratch_bytes(n)
 size_t  sort_scratch_bytes(uint64_t n);
