@@ -98,6 +98,22 @@ def test_self_with_distinct_arrays(oracle):
     assert np.array_equal(got1.id[0], exp["id"][0])
 
 
+def test_nth1_duplicates_unordered_cells(oracle):
+    """nth=1 runs on cells left in arrival order; exact ties (duplicated points) must still resolve
+    to the smallest row, forward and reverse, as the reference's ascending in-cell order does."""
+    ra2, dec2 = G.c1(35, 40_000)
+    ra2[20_000:] = ra2[:20_000]; dec2[20_000:] = dec2[:20_000]
+    ra1, dec1 = G.c1(36, 30_000)
+    ra1[15_000:] = ra1[:15_000]; dec1[15_000:] = dec1[:15_000]
+    exp = oracle.oracle_qxmatch(ra1, dec1, ra2, dec2, thread=8)
+    for _ in range(3):                                   # atomics make the cell order vary run to run
+        got = qxmatch(ra1, dec1, ra2, dec2)
+        assert_same_result(got, exp, RTOL, "dups-nth1")
+    assert got.stats["rows_refined_fwd"] >= 30_000       # every tie went through the exact kernel
+    exps = oracle.oracle_qxmatch(ra2, dec2, ra2, dec2, thread=8, self=True)
+    assert_same_result(qxmatch(ra2, dec2), exps, RTOL, "dups-self-nth1")
+
+
 def test_bucket_and_radix_index_agree(monkeypatch):
     """The counting-sort index (default) and the stable radix-sort index must give identical bits."""
     ra1, dec1 = G.c1(31, 80_000); ra2, dec2 = G.c1(32, 70_000)

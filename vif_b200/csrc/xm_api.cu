@@ -125,18 +125,20 @@ struct SortedCat {
 // One catalog -> cell-ordered records + CSR offsets. use_bucket: counting-sort placement
 // (xm_bucket.cu); otherwise keys -> stable radix sort -> gather (no limit on cell occupancy).
 int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
-                    uint32_t ncell, bool use_bucket, uint32_t* overflow, SortedCat& out, cudaStream_t s,
+                    uint32_t ncell, bool use_bucket, bool order_cells, uint32_t* overflow, SortedCat& out,
+                    cudaStream_t s,
                     Error& err, uint64_t* launches, cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
     XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
     XM_CUDA_TRY(out.cell.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
     int32_t rc;
     if (use_bucket) {
-        Scratch tmp, cursor, aux;
-        XM_CUDA_TRY(tmp.alloc((size_t)n*sizeof(Rec), s));
-        XM_CUDA_TRY(cursor.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
+        Scratch tmp, rank, aux;
+        if (order_cells) XM_CUDA_TRY(tmp.alloc((size_t)n*sizeof(Rec), s));
+        XM_CUDA_TRY(rank.alloc((size_t)n*sizeof(uint32_t), s));
         XM_CUDA_TRY(aux.alloc(bucket_scan_aux_bytes(ncell), s));
-        rc = launch_bucket_index(ra, dec, n, g, ncell, tmp.as<Rec>(), out.rec.as<Rec>(), out.cell.as<uint32_t>(),
-                                 cursor.as<uint32_t>(), aux.as<uint32_t>(), overflow, s, err, launches);
+        rc = launch_bucket_index(ra, dec, n, g, ncell, order_cells, tmp.as<Rec>(), out.rec.as<Rec>(),
+                                 out.cell.as<uint32_t>(), rank.as<uint32_t>(), aux.as<uint32_t>(), overflow, s,
+                                 err, launches);
         if (rc) return rc;
         if (ev_keys) XM_CUDA_TRY(cudaEventRecord(ev_keys, s));
         if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
@@ -330,28 +332,32 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         g.ccen_row = ccen.as<double>();
         if (!linear && (rc = launch_row_tables(g, cmin.as<double>(), ccen.as<double>(), s, err, &launches))) return rc;
 
+        // qxmatch.hpp:383-387: nth is lowered to n2 after allocation; planes >= n2 keep npos / NaN
+        const uint32_t nth_eff = (uint32_t)(n2 < nth ? n2 : nth);
+        const int self_mode = self ? (same_cat ? 1 : 2) : 0;
+        // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
+        // the rows it flags (list length stays on the device: no host round trip)
+        const bool fast = !P.exact_only && fast_path_applicable(g) && self_mode != 2;
+        // Nearest-neighbour-only calls never depend on the order inside a cell (the filter flags
+        // every tie, the K=1 exact kernel breaks in-cell ties by row), so the bucket index may
+        // leave cells in arrival order.
+        const bool unordered = use_bucket && fast && nth_eff == 1;
         SortedCat s1, s2;
-        if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, use_bucket, &ctx->d_ctr->index_overflow, s1, s,
-                              err, &launches, ev[2], ev[3]))) return rc;
+        if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, use_bucket, !unordered,
+                              &ctx->d_ctr->index_overflow, s1, s, err, &launches, ev[2], ev[3]))) return rc;
         const CatView* v2 = &s1.view;
         if (!same_cat) {
-            if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, use_bucket, &ctx->d_ctr->index_overflow, s2,
-                                  s, err, &launches, nullptr, nullptr))) return rc;
+            if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, use_bucket, !unordered,
+                                  &ctx->d_ctr->index_overflow, s2, s, err, &launches, nullptr, nullptr))) return rc;
             v2 = &s2.view;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[5], s));
 
-        // qxmatch.hpp:383-387: nth is lowered to n2 after allocation; planes >= n2 keep npos / NaN
-        const uint32_t nth_eff = (uint32_t)(n2 < nth ? n2 : nth);
         if (nth_eff < nth) {
             if ((rc = launch_fill_outputs(id, d, nth*n1, linear ? dinf : dnan, s, err, &launches))) return rc;
         }
         // `self` with two different arrays is legal in the reference (i == j skipped by index);
         // the shared-index shortcut (slot equality) only applies when the arrays are the same
-        const int self_mode = self ? (same_cat ? 1 : 2) : 0;
-        // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
-        // the rows it flags (list length stays on the device: no host round trip)
-        const bool fast = !P.exact_only && fast_path_applicable(g) && self_mode != 2;
         Scratch refine, resrec;
         if (fast) {
             XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
@@ -361,11 +367,11 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
             if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
-                                               (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s,
+                                               (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
                                                err, &launches))) return rc;
         } else {
             if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, nth_eff, n1, id, d, nullptr,
-                                               (uint32_t)n1, nullptr, false, ctx->d_ctr, s, err, &launches))) return rc;
+                                               (uint32_t)n1, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
         if (mirror) {
@@ -375,11 +381,11 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                                     &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
                                                        refine.as<uint32_t>(), (uint32_t)n2,
-                                                       &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err,
+                                                       &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr, s, err,
                                                        &launches))) return rc;
                 } else {
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd, nullptr,
-                                                       (uint32_t)n2, nullptr, true, ctx->d_ctr, s, err, &launches))) return rc;
+                                                       (uint32_t)n2, nullptr, true, false, ctx->d_ctr, s, err, &launches))) return rc;
                 }
             } else {
                 // reverse pass skipped (qxmatch.hpp:395): rid = npos, rd = proxy_to_true(inf)

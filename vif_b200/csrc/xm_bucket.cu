@@ -3,12 +3,14 @@
 // The reference pushes row ids into per-cell vectors in ascending row order. Rebuilt here as a
 // counting sort whose every pass streams (no random 8-byte gathers, only full-sector scatters):
 //   1. count:  one pass over (ra, dec): cell key (IEEE subtract/divide/floor as the reference),
-//              atomicAdd on the per-cell counter (the table is L2-resident);
+//              atomicAdd on the per-cell counter (the table is L2-resident); the returned value is
+//              kept as the row's arrival rank;
 //   2. scan:   exclusive prefix sum of the counters -> CSR offsets cstart[ncell+1];
-//   3. place:  second pass over (ra, dec): slot = cstart[key] + atomicAdd(cursor[key], 1); the
-//              source's 32-byte record (radians, cos(dec), row, key) is written to that slot -- a
+//   3. place:  second pass over (ra, dec): slot = cstart[key] + the rank the counting atomic returned
+//              in pass 1; the source's 32-byte record (radians, cos(dec), row, key) is written to that slot -- a
 //              scattered store of one full DRAM sector, no read-modify-write;
-//   4. order:  atomics fill a cell in arbitrary order, the reference's order inside a cell is
+//   4. order (skipped for nearest-neighbour-only calls, whose kernels do not depend on the order
+//              inside a cell):  atomics fill a cell in arbitrary order, the reference's order inside a cell is
 //              ascending row (it decides exact ties): one warp per cell ranks the cell's records by
 //              row and writes them to their final slots (out of place, both sides streamed).
 // Cells holding more than kMaxCellSort rows are left unordered and reported through *overflow; the
@@ -31,12 +33,31 @@ __device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridVi
     return ix*g.ndec + iy;
 }
 
+constexpr int kRows = 4;     // rows per thread: independent loads / atomics in flight
+
+// pass 1: per-cell counters; the value the atomic returns is the row's arrival rank in its cell
 __global__ void __launch_bounds__(kThreads)
 count_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
-             uint32_t* __restrict__ count) {
-    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    atomicAdd(count + cell_key(__ldg(ra + i), __ldg(dec + i), g), 1u);
+             uint32_t* __restrict__ count, uint32_t* __restrict__ rank) {
+    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
+    double r[kRows], d[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        r[k] = i < n ? __ldg(ra + i) : 0.0;
+        d[k] = i < n ? __ldg(dec + i) : 0.0;
+    }
+    uint32_t rk[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        rk[k] = i < n ? atomicAdd(count + cell_key(r[k], d[k], g), 1u) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        if (i < n) rank[i] = rk[k];
+    }
 }
 
 // ---- exclusive scan of u32 (three-level, in place) ------------------------------------------------
@@ -98,20 +119,36 @@ void exclusive_scan(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, u
 }
 
 // ---- placement --------------------------------------------------------------------------------------
+// pass 2: slot = cstart[key] + arrival rank; one full-sector store per source, no atomics
 __global__ void __launch_bounds__(kThreads)
 place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
-             const uint32_t* __restrict__ cstart, uint32_t* __restrict__ cursor, Rec* __restrict__ out) {
-    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double r = __ldg(ra + i), d = __ldg(dec + i);
-    const uint32_t key = cell_key(r, d, g);
-    const uint32_t slot = cstart[key] + atomicAdd(cursor + key, 1u);
-    double x, y, c;
-    if (g.linear) { x = r; y = d; c = 1.0; }
-    else { y = __dmul_rn(d, XM_D2R); x = __dmul_rn(r, XM_D2R); c = cos(y); }     // qxmatch.hpp:174-180
-    const unsigned long long w = (unsigned long long)i | ((unsigned long long)key << 32);
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(out + slot), "l"(__double_as_longlong(x)),
-                 "l"(__double_as_longlong(y)), "l"(__double_as_longlong(c)), "l"(w) : "memory");
+             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ rank, Rec* __restrict__ out) {
+    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
+    double r[kRows], d[kRows];
+    uint32_t rk[kRows], key[kRows], slot[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        r[k] = i < n ? __ldg(ra + i) : 0.0;
+        d[k] = i < n ? __ldg(dec + i) : 0.0;
+        rk[k] = i < n ? __ldg(rank + i) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        key[k] = cell_key(r[k], d[k], g);
+        slot[k] = __ldg(cstart + key[k]) + rk[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        if (i >= n) continue;
+        double x, y, c;
+        if (g.linear) { x = r[k]; y = d[k]; c = 1.0; }
+        else { y = __dmul_rn(d[k], XM_D2R); x = __dmul_rn(r[k], XM_D2R); c = cos(y); }   // qxmatch.hpp:174-180
+        const unsigned long long w = (unsigned long long)i | ((unsigned long long)key[k] << 32);
+        asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(out + slot[k]), "l"(__double_as_longlong(x)),
+                     "l"(__double_as_longlong(y)), "l"(__double_as_longlong(c)), "l"(w) : "memory");
+    }
 }
 
 // one warp per cell: rank the cell's records by original row, write them to their final slots
@@ -151,23 +188,27 @@ size_t bucket_scan_aux_bytes(uint32_t ncell) {
     return (size_t)tot*sizeof(uint32_t);
 }
 
-// rec_tmp, rec_out: n records each; cstart, cursor: ncell+1 words; aux: bucket_scan_aux_bytes(ncell);
+// rec_out: n records; rec_tmp: n records (only touched when order_cells); cstart: ncell+1 words;
+// rank: n words; aux: bucket_scan_aux_bytes(ncell). order_cells = false leaves every cell in
+// arrival order (callers that do not depend on the order inside a cell skip a full pass);
 // *overflow (device word) is incremented when a cell was too large to order.
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
-                            uint32_t ncell, Rec* rec_tmp, Rec* rec_out, uint32_t* cstart,
-                            uint32_t* cursor, uint32_t* aux, uint32_t* overflow, cudaStream_t s,
-                            Error& err, uint64_t* launches) {
+                            uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
+                            uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
+                            cudaStream_t s, Error& err, uint64_t* launches) {
     XM_CUDA_TRY(cudaMemsetAsync(cstart, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
-    XM_CUDA_TRY(cudaMemsetAsync(cursor, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
-    const uint32_t blocks = (n + kThreads - 1)/kThreads;
-    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart);
+    const uint32_t blocks = (n + kThreads*kRows - 1)/(kThreads*kRows);
+    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank);
     *launches += 1;
     exclusive_scan(cstart, ncell + 1, aux, s, launches);
-    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, cursor, rec_tmp);
-    const uint64_t threads = (uint64_t)ncell*32;
-    order_cells_kernel<<<(unsigned)((threads + kThreads - 1)/kThreads), kThreads, 0, s>>>(rec_tmp, cstart, ncell,
-                                                                                        rec_out, overflow);
-    *launches += 2;
+    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank, order_cells ? rec_tmp : rec_out);
+    *launches += 1;
+    if (order_cells) {
+        const uint64_t threads = (uint64_t)ncell*32;
+        order_cells_kernel<<<(unsigned)((threads + kThreads - 1)/kThreads), kThreads, 0, s>>>(rec_tmp, cstart, ncell,
+                                                                                            rec_out, overflow);
+        *launches += 1;
+    }
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
 }

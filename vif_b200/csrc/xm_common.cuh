@@ -88,9 +88,9 @@ int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, con
 // xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
 size_t  bucket_scan_aux_bytes(uint32_t ncell);
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
-                            uint32_t ncell, Rec* rec_tmp, Rec* rec_out, uint32_t* cstart,
-                            uint32_t* cursor, uint32_t* aux, uint32_t* overflow, cudaStream_t s,
-                            Error& err, uint64_t* launches);
+                            uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
+                            uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
+                            cudaStream_t s, Error& err, uint64_t* launches);
 // xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
 // by sort_scratch_bytes(n)
 size_t  sort_scratch_bytes(uint64_t n);
@@ -103,8 +103,8 @@ int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const Ca
                                  int self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
                                  uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
-                                 SearchCounters* ctr, cudaStream_t s, Error& err,
-                                 uint64_t* launches);
+                                 bool cells_unordered, SearchCounters* ctr, cudaStream_t s,
+                                 Error& err, uint64_t* launches);
 int32_t launch_row_tables(const GridView& g, double* cmin_row, double* ccen_row, cudaStream_t s,
                           Error& err, uint64_t* launches);
 // xm_search_fast.cu: nearest-neighbour filter kernel (nth = 1, spherical, rings 0-1); rows it cannot

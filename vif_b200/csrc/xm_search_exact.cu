@@ -59,6 +59,7 @@ struct RegList {
     }
     __device__ __forceinline__ double get_d(int k) const { return d[k]; }
     __device__ __forceinline__ uint32_t get_q(int k) const { return q[k]; }
+    __device__ __forceinline__ void set0(double sd, uint32_t cq) { d[0] = sd; q[0] = cq; }
 };
 
 // nth > 8: the list lives in the output planes themselves (proxy in d, candidate slot in id)
@@ -92,6 +93,7 @@ struct MemList {
     }
     __device__ __forceinline__ double get_d(int k) const { return d[(uint64_t)k*stride]; }
     __device__ __forceinline__ uint32_t get_q(int k) const { return (uint32_t)q[(uint64_t)k*stride]; }
+    __device__ __forceinline__ void set0(double sd, uint32_t cq) { d[0] = sd; q[0] = cq; }
 };
 
 // 0 < |a-b| <= 8 ulp: an ordering that a libm differing in the last bits could flip
@@ -138,7 +140,11 @@ __device__ __forceinline__ double cell_lower_bound(const GridView& g, double x1,
 }
 
 // ---- ring search ---------------------------------------------------------------------------------
-template <class List, bool LINEAR>
+// UNORD (nth = 1 only): the cells of `cand` are in arbitrary order (bucket index without the
+// ordering pass). The reference visits a cell in ascending row order and keeps the first of
+// equal proxies; the same outcome is obtained by letting an equal proxy from the SAME cell visit
+// win when its row is smaller.
+template <class List, bool LINEAR, bool UNORD>
 __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView& src,
                                                 const CatView& cand, int self_mode, uint32_t p,
                                                 List& L, unsigned long long& evals) {
@@ -169,6 +175,8 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
             const uint2 r = make_uint2(cand.cstart[ck], cand.cstart[ck + 1]);
             if (r.x == r.y) return;
             if (d > 0 && cell_lower_bound<LINEAR>(g, x1, y1, c1, cx, cy) >= L.kth()) return;
+            bool best_here = false;            // UNORD: the current best came from this cell visit
+            uint32_t best_row = 0;
             for (uint32_t q = r.x; q < r.y; ++q) {
                 // self match (qxmatch.hpp:314): skip the source itself -- same slot when both
                 // catalogs share one index (1), same original row otherwise (2)
@@ -178,7 +186,18 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
                 const double sd = LINEAR ? proxy_lin(x1, y1, cd.x, cd.y)
                                          : proxy_sph(x1, y1, c1, cd.x, cd.y, cd.c, g.sin_model);
                 ++evals;
-                L.insert(sd, q);
+                if (UNORD) {
+                    const double cur = L.get_d(0);
+                    if (sd < cur || (sd == cur && best_here && cd.idx < best_row)) {
+                        L.insert(sd < cur ? sd : -1.0, q);      // forced replacement of slot 0 ...
+                        L.set0(sd, q);                          // ... with the true proxy
+                        best_here = true; best_row = cd.idx;
+                    } else {
+                        L.insert(sd, q);                        // rejected: only updates the diagnostics
+                    }
+                } else {
+                    L.insert(sd, q);
+                }
             }
         });
         // qxmatch.hpp:336-337
@@ -197,7 +216,7 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
                          uint64_t plane_stride, uint64_t* __restrict__ id_out,
                          double* __restrict__ d_out, const uint32_t* __restrict__ rows,
                          uint32_t nrows, const unsigned long long* __restrict__ nrows_dev,
-                         int reverse, SearchCounters* ctr) {
+                         int reverse, int unordered, SearchCounters* ctr) {
     // rows == nullptr: thread t handles sorted slot t. Otherwise the kernel walks the row list with
     // a grid-stride loop; its length may live on the device (filter kernel's refine count).
     if (nrows_dev) { const unsigned long long c = *nrows_dev; nrows = c < nrows ? (uint32_t)c : nrows; }
@@ -209,7 +228,8 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
         if (K > 0) {
             RegList<(K > 0 ? K : 1)> L;
             L.init();
-            ring_search_row<RegList<(K > 0 ? K : 1)>, LINEAR>(g, src, cand, self_mode, p, L, evals);
+            if (K == 1 && unordered) ring_search_row<RegList<(K > 0 ? K : 1)>, LINEAR, (K == 1)>(g, src, cand, self_mode, p, L, evals);
+            else ring_search_row<RegList<(K > 0 ? K : 1)>, LINEAR, false>(g, src, cand, self_mode, p, L, evals);
 #pragma unroll
             for (int k = 0; k < (K > 0 ? K : 1); ++k) {
                 const uint32_t q = L.q[k];
@@ -221,7 +241,7 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
             MemList L;
             L.d = d_out + i; L.q = id_out + i; L.stride = plane_stride; L.k_eff = nth_eff;
             L.init();
-            ring_search_row<MemList, LINEAR>(g, src, cand, self_mode, p, L, evals);
+            ring_search_row<MemList, LINEAR, false>(g, src, cand, self_mode, p, L, evals);
             amb += list_ambiguous(L, nth_eff) ? 1 : 0;
             for (uint32_t k = 0; k < nth_eff; ++k) {
                 const uint32_t q = L.get_q(k);
@@ -340,12 +360,12 @@ template <bool LINEAR>
 void dispatch_ring(int K, dim3 grid, cudaStream_t s, const GridView& g, const CatView& src,
                    const CatView& cand, int self_mode, uint32_t nth_eff, uint64_t stride,
                    uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows,
-                   const unsigned long long* nrows_dev, int reverse, SearchCounters* ctr) {
+                   const unsigned long long* nrows_dev, int reverse, int unordered, SearchCounters* ctr) {
 #define XM_CASE(KK) case KK: ring_search_exact_kernel<KK, LINEAR><<<grid, kRingThreads, 0, s>>>( \
-        g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, ctr); break;
+        g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, unordered, ctr); break;
     switch (K) { XM_CASE(1) XM_CASE(2) XM_CASE(3) XM_CASE(4) XM_CASE(5) XM_CASE(6) XM_CASE(7) XM_CASE(8)
                  default: ring_search_exact_kernel<0, LINEAR><<<grid, kRingThreads, 0, s>>>(
-                     g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, ctr); }
+                     g, src, cand, self_mode, nth_eff, stride, id_out, d_out, rows, nrows, nrows_dev, reverse, unordered, ctr); }
 #undef XM_CASE
 }
 
@@ -371,17 +391,18 @@ int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const Ca
                                  int self, uint32_t nth_eff, uint64_t plane_stride,
                                  uint64_t* id_out, double* d_out, const uint32_t* rows,
                                  uint32_t nrows, const unsigned long long* nrows_dev, bool reverse,
-                                 SearchCounters* ctr, cudaStream_t s, Error& err,
-                                 uint64_t* launches) {
+                                 bool cells_unordered, SearchCounters* ctr, cudaStream_t s,
+                                 Error& err, uint64_t* launches) {
     if (nrows == 0 || nth_eff == 0) return XM_OK;
+    const int unordered = (cells_unordered && nth_eff == 1) ? 1 : 0;
     uint32_t blocks = (nrows + kRingThreads - 1)/kRingThreads;
     if (nrows_dev && blocks > 148*4) blocks = 148*4;     // list of unknown (small) length: persistent grid
     const dim3 grid(blocks);
     const int K = nth_eff <= 8 ? (int)nth_eff : 0;
     if (g.linear) dispatch_ring<true>(K, grid, s, g, src, cand, self, nth_eff, plane_stride, id_out,
-                                      d_out, rows, nrows, nrows_dev, reverse, ctr);
+                                      d_out, rows, nrows, nrows_dev, reverse, unordered, ctr);
     else dispatch_ring<false>(K, grid, s, g, src, cand, self, nth_eff, plane_stride, id_out, d_out,
-                              rows, nrows, nrows_dev, reverse, ctr);
+                              rows, nrows, nrows_dev, reverse, unordered, ctr);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
