@@ -358,13 +358,14 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         }
         // `self` with two different arrays is legal in the reference (i == j skipped by index);
         // the shared-index shortcut (slot equality) only applies when the arrays are the same
-        Scratch refine, resrec;
+        Scratch refine, resrec, plans;
         if (fast) {
             XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
             XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1 > n2 ? n1 : n2), s));
+            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1 > n2 ? n1 : n2), s));
         }
         if (fast && nth_eff == 1) {
-            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, refine.as<uint32_t>(),
+            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
             if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
                                                (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
@@ -377,7 +378,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         if (mirror) {
             if (!self) {
                 if (fast) {
-                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec.p, refine.as<uint32_t>(),
+                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec.p, plans.p, refine.as<uint32_t>(),
                                                     &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
                                                        refine.as<uint32_t>(), (uint32_t)n2,

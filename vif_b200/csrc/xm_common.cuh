@@ -111,8 +111,9 @@ int32_t launch_row_tables(const GridView& g, double* cmin_row, double* ccen_row,
 // decide rigorously are appended to refine_list (count in *refine_count) for the exact kernel
 bool    fast_path_applicable(const GridView& g);
 size_t  filter_result_bytes(uint64_t n);     // scratch for the filter's sector-sized result records
+size_t  filter_plan_bytes(uint64_t n);       // scratch for the per-tile staging plans
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
-                              uint64_t* id_out, double* d_out, void* result_scratch,
+                              uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                               SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1, const double* c1,

@@ -27,7 +27,7 @@ namespace xm {
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000ll); }
 
@@ -138,9 +138,63 @@ __device__ __forceinline__ void merge_best(Best& b, int32_t a1, int32_t a2, uint
     b.slot = better ? aslot : b.slot;
 }
 
-constexpr int kMaxItems = 4*kThreads;    // ring-1 work items a CTA can queue (4 per source; typical total ~90)
-constexpr int kStageCap = 768;           // candidate records a CTA can stage (24 KB; typical need ~450)
-constexpr int kStageRows = 40;           // cell rows (incl. halo) a staged block may span
+constexpr int kQueuePerSrc = 2;          // ring-1 cells a source may queue; further ones are scanned in place
+constexpr int kMaxItems = kQueuePerSrc*kThreads;   // typical total: ~0.7 per source
+constexpr int kStageCap = 1024;          // candidate records a CTA can stage (32 KB; typical need ~800)
+constexpr int kStageRows = 64;           // cell rows (incl. halo) a staged block may span
+
+// Per-tile staging plan, written by plan_tiles_kernel once per search: where the three column runs
+// of the tile's neighbourhood start in the cell-ordered candidate array.
+struct __align__(16) TilePlan {
+    uint32_t run_start[3];
+    uint32_t run_cnt[3];
+    int32_t  ya;                 // first staged cell row
+    uint32_t xs_nrows;           // column of the strip | staged rows << 24 (0 rows: not staged)
+};
+
+// dynamic shared memory layout of ring_nn_filter_kernel
+struct FilterSmem {
+    Rec      cand[kStageCap];
+    double   x[kThreads], y[kThreads], c[kThreads];
+    uint2    range[kMaxItems];
+    int32_t  shift[kMaxItems];
+    int32_t  a1[kMaxItems], a2[kMaxItems];
+    uint32_t slot[kMaxItems];
+    uint32_t cs[3][kStageRows + 1];
+    uint64_t bar;
+    uint32_t warp_tot[kThreads/32];
+    uint8_t  owner[kMaxItems];
+};
+
+__global__ void __launch_bounds__(256)
+plan_tiles_kernel(GridView g, CatView src, CatView cand, uint32_t ntiles, TilePlan* __restrict__ plan) {
+    const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t p0 = t*kThreads, p1 = min(p0 + (uint32_t)kThreads, src.n) - 1;
+    const uint32_t kf = src.rec[p0].key, kl = src.rec[p1].key;
+    const int ndec = (int)g.ndec, nra = (int)g.nra;
+    const int xs = (int)(kf/g.ndec), yf = (int)(kf - (uint32_t)xs*g.ndec);
+    const int xl = (int)(kl/g.ndec), yl = (int)(kl - (uint32_t)xl*g.ndec);
+    const int ya = max(yf - 1, 0), yb = min(yl + 1, ndec - 1);
+    const int nrows = yb - ya + 1;
+    TilePlan pl;
+    pl.ya = ya; pl.xs_nrows = 0;
+    for (int c = 0; c < 3; ++c) { pl.run_start[c] = 0; pl.run_cnt[c] = 0; }
+    if (xs == xl && nrows <= kStageRows && xs < (1 << 24)) {
+        uint32_t tot = 0;
+        for (int c = 0; c < 3; ++c) {
+            const int cx = xs - 1 + c;
+            if (cx < 0 || cx >= nra) continue;
+            const uint32_t b0 = cand.cstart[(uint32_t)cx*g.ndec + (uint32_t)ya];
+            const uint32_t b1 = cand.cstart[(uint32_t)cx*g.ndec + (uint32_t)(ya + nrows)];
+            pl.run_start[c] = b0; pl.run_cnt[c] = b1 - b0;
+            tot += b1 - b0;
+        }
+        if (tot <= (uint32_t)kStageCap) pl.xs_nrows = (uint32_t)xs | ((uint32_t)nrows << 24);
+    }
+    plan[t] = pl;
+}
+
 constexpr int32_t kNotStaged = INT32_MIN;
 
 // ---- TMA bulk copy (1-D, no tensor map) + mbarrier ------------------------------------------------
@@ -180,23 +234,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 //   4. every thread merges the partial results of its own source, applies the stop rule of ring 1
 //      and the ambiguity test, and writes id / d (or queues the row for the exact kernel).
 template <bool SELF>
-__global__ void __launch_bounds__(kThreads)
-ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict__ res,
-                      uint32_t* __restrict__ refine_list, unsigned long long* refine_count,
-                      int reverse, SearchCounters* ctr) {
-    __shared__ __align__(128) Rec s_cand[kStageCap];
-    __shared__ uint32_t s_cs[3][kStageRows + 1];        // CSR offsets of the staged block, per column
-    __shared__ int32_t  s_delta[3];                     // slot -> stage index shift, per column
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_klast;
-    __shared__ int      s_staged;
-    __shared__ double s_x[kThreads], s_y[kThreads], s_c[kThreads];
-    __shared__ uint8_t  s_owner[kMaxItems];             // thread that owns the queued (source, cell) pair
-    __shared__ uint2    s_range[kMaxItems];             // candidate slots of the cell
-    __shared__ int32_t  s_shift[kMaxItems];             // stage shift of the cell, kNotStaged = global
-    __shared__ int32_t  s_a1[kMaxItems], s_a2[kMaxItems];
-    __shared__ uint32_t s_slot[kMaxItems];
-    __shared__ uint32_t s_warp_tot[kThreads/32];
+__global__ void __launch_bounds__(kThreads, 4)
+ring_nn_filter_kernel(GridView g, CatView src, CatView cand, const TilePlan* __restrict__ plan,
+                      ResRec* __restrict__ res, uint32_t* __restrict__ refine_list,
+                      unsigned long long* refine_count, int reverse, SearchCounters* ctr) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FilterSmem& sm = *reinterpret_cast<FilterSmem*>(smem_raw);
+    Rec* const s_cand = sm.cand;
 
     const uint32_t p0 = blockIdx.x*blockDim.x;
     const uint32_t p = p0 + threadIdx.x;
@@ -205,57 +249,46 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict_
     const int ndec = (int)g.ndec, nra = (int)g.nra;
     uint32_t evals = 0;
 
+    // ---- 0. stage the neighbourhood (plan and own record are loaded together) ---------------------
+    const uint4 pa = __ldg(reinterpret_cast<const uint4*>(plan + blockIdx.x));
+    const uint4 pb = __ldg(reinterpret_cast<const uint4*>(plan + blockIdx.x) + 1);
     Rec me;
     me.x = me.y = me.c = 0.0; me.idx = 0; me.key = 0;
     if (live) me = load_rec(src.rec + p);
-    const uint32_t nlive = min((uint32_t)kThreads, src.n - p0);
-    if (threadIdx.x == nlive - 1) s_klast = me.key;
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // first key of the strip: thread 0's
-    const uint32_t kfirst = __shfl_sync(0xffffffffu, me.key, 0);
-    __shared__ uint32_t s_kfirst;
-    if (threadIdx.x == 0) s_kfirst = kfirst;
     __syncthreads();
 
-    // ---- 0. stage the neighbourhood -------------------------------------------------------------------
-    const uint32_t kf = s_kfirst, kl = s_klast;
-    const int xs = (int)(kf/g.ndec), yf = (int)(kf - (uint32_t)xs*g.ndec);
-    const int xl = (int)(kl/g.ndec), yl = (int)(kl - (uint32_t)xl*g.ndec);
-    const int ya = max(yf - 1, 0), yb = min(yl + 1, ndec - 1);
-    const int nrows = yb - ya + 1;
-    const bool try_stage = (xs == xl) && nrows <= kStageRows;
-    if (try_stage) {
+    const uint32_t run_start[3] = {pa.x, pa.y, pa.z};
+    const uint32_t run_cnt[3] = {pa.w, pb.x, pb.y};
+    const int ya = (int)pb.z;
+    const int nrows = (int)(pb.w >> 24);
+    const int xs = (int)(pb.w & 0xffffffu);
+    const bool staged_plan = nrows > 0;
+    const uint32_t tot = run_cnt[0] + run_cnt[1] + run_cnt[2];
+    int32_t delta[3];
+    delta[0] = -(int32_t)run_start[0];
+    delta[1] = (int32_t)run_cnt[0] - (int32_t)run_start[1];
+    delta[2] = (int32_t)(run_cnt[0] + run_cnt[1]) - (int32_t)run_start[2];
+    if (staged_plan) {
+        if (threadIdx.x == 0 && tot) {
+            mbar_expect_tx(&sm.bar, tot*(uint32_t)sizeof(Rec));
+            uint32_t off = 0;
+#pragma unroll
+            for (int col = 0; col < 3; ++col) {
+                if (run_cnt[col]) bulk_g2s(&s_cand[off], cand.rec + run_start[col], run_cnt[col]*(uint32_t)sizeof(Rec), &sm.bar);
+                off += run_cnt[col];
+            }
+        }
         for (int t = threadIdx.x; t < 3*(nrows + 1); t += kThreads) {
             const int col = t/(nrows + 1), r = t - col*(nrows + 1);
             const int cx = xs - 1 + col;
-            s_cs[col][r] = (cx >= 0 && cx < nra) ? cand.cstart[(uint32_t)cx*g.ndec + (uint32_t)(ya + r)] : 0u;
+            sm.cs[col][r] = (cx >= 0 && cx < nra) ? cand.cstart[(uint32_t)cx*g.ndec + (uint32_t)(ya + r)] : 0u;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int staged = 0;
-        if (try_stage) {
-            uint32_t tot = 0;
-            for (int col = 0; col < 3; ++col) tot += s_cs[col][nrows] - s_cs[col][0];
-            if (tot <= (uint32_t)kStageCap) {
-                staged = 1;
-                uint32_t off = 0;
-                if (tot) mbar_expect_tx(&s_bar, tot*(uint32_t)sizeof(Rec));
-                for (int col = 0; col < 3; ++col) {
-                    const uint32_t b0 = s_cs[col][0], cnt = s_cs[col][nrows] - b0;
-                    s_delta[col] = (int32_t)off - (int32_t)b0;
-                    if (cnt) bulk_g2s(&s_cand[off], cand.rec + b0, cnt*(uint32_t)sizeof(Rec), &s_bar);
-                    off += cnt;
-                }
-                if (!tot) staged = 2;                   // nothing to wait for
-            }
-        }
-        s_staged = staged;
-    }
-    __syncthreads();
-    const int staged = s_staged;
-    if (staged == 1) mbar_wait(&s_bar, 0);
+    const int staged = staged_plan ? 1 : 0;
+    if (staged && tot) mbar_wait(&sm.bar, 0);
 
     Best b;
     b.h1 = kInfHi; b.h2 = kInfHi; b.slot = 0xffffffffu;
@@ -265,13 +298,13 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict_
     double cdist = 0.0;
 
     if (live) {
-        if (xs == xl) x0 = xs; else x0 = (int)(me.key/g.ndec);     // one-column strips skip the division
+        if (staged) x0 = xs; else x0 = (int)(me.key/g.ndec);       // one-column strips skip the division
         y0 = (int)(me.key - (uint32_t)x0*g.ndec);
         const double x1 = me.x, y1 = me.y, c1 = me.c;
         // ---- 1. ring 0: own cell ---------------------------------------------------------------------
         if (staged) {
-            const uint32_t qs = s_cs[1][y0 - ya], qe = s_cs[1][y0 - ya + 1];
-            scan_range_staged<SELF>(s_cand, s_delta[1], qs, qe, x1, y1, c1, p, b);
+            const uint32_t qs = sm.cs[1][y0 - ya], qe = sm.cs[1][y0 - ya + 1];
+            scan_range_staged<SELF>(s_cand, delta[1], qs, qe, x1, y1, c1, p, b);
             evals += qe - qs;
         } else {
             const uint32_t qs = cand.cstart[me.key], qe = cand.cstart[me.key + 1];
@@ -326,9 +359,9 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict_
     // ---- 2. queue the surviving (source, cell) pairs ---------------------------------------------------
     // The owner resolves each cell's slot range (from the staged CSR offsets when the cell is inside
     // the staged block) and queues only non-empty cells.
-    s_x[threadIdx.x] = me.x; s_y[threadIdx.x] = me.y; s_c[threadIdx.x] = me.c;
-    uint2 rng[4];
-    int32_t shf[4];
+    sm.x[threadIdx.x] = me.x; sm.y[threadIdx.x] = me.y; sm.c[threadIdx.x] = me.c;
+    uint2 rng[kQueuePerSrc];
+    int32_t shf[kQueuePerSrc];
     uint32_t cnt = 0;
     {
         uint32_t m = mask;
@@ -339,21 +372,20 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict_
             const int ry = y0 + by - ya;
             uint2 r; int32_t sh;
             if (staged && bx >= -1 && bx <= 1 && ry >= 0 && ry < nrows) {
-                r = make_uint2(s_cs[bx + 1][ry], s_cs[bx + 1][ry + 1]);
-                sh = s_delta[bx + 1];
+                r = make_uint2(sm.cs[bx + 1][ry], sm.cs[bx + 1][ry + 1]);
+                sh = bx < 0 ? delta[0] : (bx > 0 ? delta[2] : delta[1]);
             } else {
                 const uint32_t ck = (uint32_t)((int)me.key + bx*ndec + by);
                 r = make_uint2(cand.cstart[ck], cand.cstart[ck + 1]);
                 sh = kNotStaged;
             }
             if (r.x == r.y) continue;
-            if (cnt < 4) {
+            if (cnt < (uint32_t)kQueuePerSrc) {
                 // static indexing keeps rng[] / shf[] in registers
-                if (cnt == 0) { rng[0] = r; shf[0] = sh; } else if (cnt == 1) { rng[1] = r; shf[1] = sh; }
-                else if (cnt == 2) { rng[2] = r; shf[2] = sh; } else { rng[3] = r; shf[3] = sh; }
+                if (cnt == 0) { rng[0] = r; shf[0] = sh; } else { rng[1] = r; shf[1] = sh; }
                 ++cnt;
             } else {
-                // more than 4 non-empty cells for one source: scan the rest in place
+                // more cells than a source may queue: scan the rest in place
                 if (sh != kNotStaged) scan_range_staged<SELF>(s_cand, sh, r.x, r.y, me.x, me.y, me.c, p, b);
                 else scan_range<SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, p, b);
                 evals += r.y - r.x;
@@ -366,37 +398,37 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, ResRec* __restrict_
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (lane == 31) s_warp_tot[wid] = inc;
+    if (lane == 31) sm.warp_tot[wid] = inc;
     __syncthreads();
     uint32_t first = inc - cnt, total = 0;
 #pragma unroll
     for (int k = 0; k < kThreads/32; ++k) {
-        if (k < wid) first += s_warp_tot[k];
-        total += s_warp_tot[k];
+        if (k < wid) first += sm.warp_tot[k];
+        total += sm.warp_tot[k];
     }
-    // total <= 4*kThreads = kMaxItems by construction
+    // total <= kMaxItems by construction
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kQueuePerSrc; ++k) {
         if ((uint32_t)k < cnt) {
-            s_owner[first + k] = (uint8_t)threadIdx.x; s_range[first + k] = rng[k]; s_shift[first + k] = shf[k];
+            sm.owner[first + k] = (uint8_t)threadIdx.x; sm.range[first + k] = rng[k]; sm.shift[first + k] = shf[k];
         }
     }
     __syncthreads();
 
     // ---- 3. one queued pair per thread ------------------------------------------------------------------
     for (uint32_t it = threadIdx.x; it < total; it += kThreads) {
-        const int owner = s_owner[it];
-        const uint2 r = s_range[it];
-        const int32_t sh = s_shift[it];
+        const int owner = sm.owner[it];
+        const uint2 r = sm.range[it];
+        const int32_t sh = sm.shift[it];
         Best a;
         a.h1 = kInfHi; a.h2 = kInfHi; a.slot = 0xffffffffu;
-        if (sh != kNotStaged) scan_range_staged<SELF>(s_cand, sh, r.x, r.y, s_x[owner], s_y[owner], s_c[owner], p0 + owner, a);
-        else scan_range<SELF>(cand.rec, r.x, r.y, s_x[owner], s_y[owner], s_c[owner], p0 + owner, a);
+        if (sh != kNotStaged) scan_range_staged<SELF>(s_cand, sh, r.x, r.y, sm.x[owner], sm.y[owner], sm.c[owner], p0 + owner, a);
+        else scan_range<SELF>(cand.rec, r.x, r.y, sm.x[owner], sm.y[owner], sm.c[owner], p0 + owner, a);
         evals += r.y - r.x;
-        s_a1[it] = a.h1; s_a2[it] = a.h2; s_slot[it] = a.slot;
+        sm.a1[it] = a.h1; sm.a2[it] = a.h2; sm.slot[it] = a.slot;
     }
     __syncthreads();
-    for (uint32_t k = 0; k < cnt; ++k) merge_best(b, s_a1[first + k], s_a2[first + k], s_slot[first + k]);
+    for (uint32_t k = 0; k < cnt; ++k) merge_best(b, sm.a1[first + k], sm.a2[first + k], sm.slot[first + k]);
 
     // ---- 4. decide ----------------------------------------------------------------------------------------
     if (live) {
@@ -454,21 +486,30 @@ bool fast_path_applicable(const GridView& g) {
 }
 
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
-                              uint64_t* id_out, double* d_out, void* result_scratch,
+                              uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                               SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches) {
     if (src.n == 0) return XM_OK;
-    const dim3 grid((src.n + kThreads - 1)/kThreads);
+    const uint32_t ntiles = (src.n + kThreads - 1)/kThreads;
     ResRec* res = (ResRec*)result_scratch;
-    if (self) ring_nn_filter_kernel<true><<<grid, kThreads, 0, s>>>(g, src, cand, res, refine_list,
-                                                                   refine_count, reverse ? 1 : 0, ctr);
-    else ring_nn_filter_kernel<false><<<grid, kThreads, 0, s>>>(g, src, cand, res, refine_list,
-                                                                refine_count, reverse ? 1 : 0, ctr);
+    TilePlan* plan = (TilePlan*)plan_scratch;
+    // > 48 KB of dynamic shared memory is an opt-in, per device
+    if (self) XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)sizeof(FilterSmem)));
+    else XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(FilterSmem)));
+    plan_tiles_kernel<<<(ntiles + 255)/256, 256, 0, s>>>(g, src, cand, ntiles, plan);
+    if (self) ring_nn_filter_kernel<true><<<ntiles, kThreads, sizeof(FilterSmem), s>>>(
+        g, src, cand, plan, res, refine_list, refine_count, reverse ? 1 : 0, ctr);
+    else ring_nn_filter_kernel<false><<<ntiles, kThreads, sizeof(FilterSmem), s>>>(
+        g, src, cand, plan, res, refine_list, refine_count, reverse ? 1 : 0, ctr);
     // rows flagged for the exact kernel carry garbage here; it overwrites them afterwards
     unpack_results_kernel<<<(src.n + 255)/256, 256, 0, s>>>(res, src.n, id_out, d_out);
-    *launches += 2;
+    *launches += 3;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
 }
+
+size_t filter_plan_bytes(uint64_t n) { return (size_t)((n + kThreads - 1)/kThreads)*sizeof(TilePlan); }
 
 }  // namespace xm
