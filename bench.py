@@ -168,8 +168,8 @@ def run_gpu_arm(args):
         ra2 = torch.empty(n2, dtype=torch.float64, device=dev)
         dec2 = torch.empty(n2, dtype=torch.float64, device=dev)
     params = QxmatchParams(nth=1, device=local)
-    stats_acc = {"ms_forward": 0.0, "ms_reverse": 0.0, "ms_total": 0.0, "ms_index": 0.0, "ms_sort": 0.0,
-                 "launches": 0, "evals": 0, "steps": 0}
+    stats_acc = {"ms_forward": 0.0, "ms_reverse": 0.0, "ms_search": 0.0, "ms_total": 0.0, "ms_index": 0.0,
+                 "ms_bbox": 0.0, "launches": 0, "evals": 0, "steps": 0}
 
     def step(record):
         from vif_b200.qxmatch import last_stats
@@ -180,7 +180,7 @@ def run_gpu_arm(args):
             out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
         if record:
             st = last_stats(local)
-            for k in ("ms_forward", "ms_reverse", "ms_total", "ms_index", "ms_sort"):
+            for k in ("ms_forward", "ms_reverse", "ms_search", "ms_total", "ms_index", "ms_bbox"):
                 stats_acc[k] += st[k]
             stats_acc["launches"] += st["launches"]
             stats_acc["evals"] += st["evals_fwd"] + st["evals_rev"]
@@ -274,7 +274,8 @@ def run_gpu_arm(args):
         bytes_fwd = 16 * nsrc_f + 16 * ncand_f + 16 * nsrc_f
         bytes_rev = 16 * n2 + 16 * nsrc_f + 16 * n2
         ms_f, ms_r = stats_acc["ms_forward"] / ns, stats_acc["ms_reverse"] / ns
-        achieved = (bytes_fwd + bytes_rev) / ((ms_f + ms_r) * 1e-3) / 1e9 if (ms_f + ms_r) > 0 else 0.0
+        ms_s = stats_acc["ms_search"] / ns          # forward and reverse launches overlap on two streams
+        achieved = (bytes_fwd + bytes_rev) / (ms_s * 1e-3) / 1e9 if ms_s > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ring_search_traffic.json")
         if os.path.exists(tp):
@@ -295,14 +296,14 @@ def run_gpu_arm(args):
                     "ms_per_step": dt.item() * 1e3, "steps": e2e_steps},
             "gpu_launches": int(launches.item()),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ring_search (forward + reverse launches)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "ring_nn_filter_kernel (forward + reverse launches, run concurrently)", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_launch": {"forward": bytes_fwd, "reverse": bytes_rev},
-                         "ms_per_launch": {"forward": ms_f, "reverse": ms_r},
+                         "ms_per_launch": {"forward": ms_f, "reverse": ms_r, "both_overlapped": ms_s},
                          "whole_path": {"bytes": whole_bytes, "GBps": whole_bytes / (ms_step * 1e-3) / 1e9,
                                         "frac": whole_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                         "stage_ms": {k: stats_acc[k] / ns for k in ("ms_total", "ms_index", "ms_sort", "ms_forward", "ms_reverse")},
+                         "stage_ms": {k: stats_acc[k] / ns for k in ("ms_total", "ms_bbox", "ms_index", "ms_search", "ms_forward", "ms_reverse")},
                          "distance_evals_per_step": stats_acc["evals"] / ns},
         }
         if world == 1 and not args.no_cpu:

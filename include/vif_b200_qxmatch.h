@@ -85,7 +85,8 @@ typedef struct xm_grid {
 typedef struct xm_stats {
     xm_grid  grid;
     double   ms_total;                 /* whole device pipeline                                    */
-    double   ms_bbox, ms_keys, ms_sort, ms_index, ms_forward, ms_reverse, ms_refine;
+    double   ms_bbox, ms_keys, ms_sort, ms_index, ms_forward, ms_reverse;
+    double   ms_search;                /* forward + reverse searches, wall (they overlap on two streams) */
     uint64_t launches;                 /* kernels launched by this library during the call         */
     uint64_t rows_refined_fwd;         /* rows the filter kernel handed to the exact kernel        */
     uint64_t rows_refined_rev;

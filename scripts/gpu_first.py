@@ -31,7 +31,7 @@ def compare(tag, got, exp, rtol=1e-9):
         out.append(f"{k}: maxrel {rel:.2e} notbitequal {nbit} nan-mismatch {nanm} inf-mismatch {infm}")
     st = got.stats
     print(f"[{'OK' if ok else 'FAIL'}] {tag}: " + "; ".join(out))
-    print(f"       refined {st['rows_refined_fwd']}/{st['rows_refined_rev']} host {st['ms_host']:.3f} total {st['ms_total']:.3f} ms (bbox {st['ms_bbox']:.3f} keys {st['ms_keys']:.3f} sort {st['ms_sort']:.3f} "
+    print(f"       refined {st['rows_refined_fwd']}/{st['rows_refined_rev']} host {st['ms_host']:.3f} total {st['ms_total']:.3f} ms (bbox {st['ms_bbox']:.3f} keys {st['ms_keys']:.3f} search {st['ms_search']:.3f} "
           f"index {st['ms_index']:.3f} fwd {st['ms_forward']:.3f} rev {st['ms_reverse']:.3f}) launches {st['launches']} "
           f"evals {st['evals_fwd']}/{st['evals_rev']} ambiguous {st['rows_ambiguous']} sin_model {st['sin_model']} "
           f"grid {st['grid']['nra']}x{st['grid']['ndec']} cs {st['grid']['cell_size']:.4f}")
@@ -108,7 +108,7 @@ def main():
     for it in range(3):
         r = qxmatch(a1, b1, a2, b2)
         st = r.stats
-        print(f"C2 1e7 dev: host {st['ms_host']:.3f} refined {st['rows_refined_fwd']}/{st['rows_refined_rev']} total {st['ms_total']:.3f} ms (bbox {st['ms_bbox']:.3f} keys {st['ms_keys']:.3f} sort {st['ms_sort']:.3f} index {st['ms_index']:.3f} "
+        print(f"C2 1e7 dev: host {st['ms_host']:.3f} refined {st['rows_refined_fwd']}/{st['rows_refined_rev']} total {st['ms_total']:.3f} ms (bbox {st['ms_bbox']:.3f} keys {st['ms_keys']:.3f} search {st['ms_search']:.3f} index {st['ms_index']:.3f} "
               f"fwd {st['ms_forward']:.3f} rev {st['ms_reverse']:.3f}) evals {st['evals_fwd']}/{st['evals_rev']} amb {st['rows_ambiguous']}")
 
 

@@ -30,7 +30,7 @@ class XmGrid(C.Structure):
 class XmStats(C.Structure):
     _fields_ = [("grid", XmGrid), ("ms_total", f64), ("ms_bbox", f64), ("ms_keys", f64),
                 ("ms_sort", f64), ("ms_index", f64), ("ms_forward", f64), ("ms_reverse", f64),
-                ("ms_refine", f64), ("launches", u64), ("rows_refined_fwd", u64),
+                ("ms_search", f64), ("launches", u64), ("rows_refined_fwd", u64),
                 ("rows_refined_rev", u64), ("rows_ambiguous", u64), ("evals_fwd", u64),
                 ("evals_rev", u64), ("sin_model", u64), ("ms_host", f64)]
 

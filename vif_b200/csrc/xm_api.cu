@@ -41,6 +41,8 @@ namespace {
 struct Context {
     int          device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // second lane: catalog-2 index, reverse search
+    cudaEvent_t  sync_ev[4];
     std::mutex   mu;
     int          sin_model = 1;
     unsigned long long* d_small = nullptr;   // 16 u64: two bounding boxes + spare
@@ -69,6 +71,8 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     c->device = device;
     memset(&c->last, 0, sizeof(c->last));
     XM_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    XM_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (auto& e : c->sync_ev) XM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     XM_CUDA_TRY(cudaMalloc(&c->d_small, 16*sizeof(unsigned long long)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_small, 16*sizeof(unsigned long long)));
     XM_CUDA_TRY(cudaMalloc(&c->d_ctr, sizeof(SearchCounters)));
@@ -342,29 +346,36 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         // every tie, the K=1 exact kernel breaks in-cell ties by row), so the bucket index may
         // leave cells in arrival order.
         const bool unordered = use_bucket && fast && nth_eff == 1;
-        SortedCat s1, s2;
+        // Two lanes: `s` indexes catalog 1 and runs the forward search, `s2` indexes catalog 2 and
+        // runs the reverse search. The lanes only meet where one needs the other's index.
+        cudaStream_t s2 = ctx->stream2;
+        cudaEvent_t* sev = ctx->sync_ev;
+        XM_CUDA_TRY(cudaEventRecord(sev[0], s));                       // inputs / row tables ready
+        XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[0], 0));
+        SortedCat s1, s2cat;
         if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, use_bucket, !unordered,
                               &ctx->d_ctr->index_overflow, s1, s, err, &launches, ev[2], ev[3]))) return rc;
         const CatView* v2 = &s1.view;
         if (!same_cat) {
             if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, use_bucket, !unordered,
-                                  &ctx->d_ctr->index_overflow, s2, s, err, &launches, nullptr, nullptr))) return rc;
-            v2 = &s2.view;
+                                  &ctx->d_ctr->index_overflow, s2cat, s2, err, &launches, nullptr, nullptr))) return rc;
+            v2 = &s2cat.view;
         }
+        XM_CUDA_TRY(cudaEventRecord(sev[1], s));                       // index of catalog 1 ready
+        XM_CUDA_TRY(cudaEventRecord(sev[2], s2));                      // index of catalog 2 ready
+        XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[2], 0));
+        XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[1], 0));
         XM_CUDA_TRY(cudaEventRecord(ev[5], s));
 
         if (nth_eff < nth) {
             if ((rc = launch_fill_outputs(id, d, nth*n1, linear ? dinf : dnan, s, err, &launches))) return rc;
         }
-        // `self` with two different arrays is legal in the reference (i == j skipped by index);
-        // the shared-index shortcut (slot equality) only applies when the arrays are the same
+        // ---- forward search (lane s) ----
         Scratch refine, resrec, plans;
-        if (fast) {
-            XM_CUDA_TRY(refine.alloc((size_t)(n1 > n2 ? n1 : n2)*4, s));
-            XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1 > n2 ? n1 : n2), s));
-            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1 > n2 ? n1 : n2), s));
-        }
         if (fast && nth_eff == 1) {
+            XM_CUDA_TRY(refine.alloc((size_t)n1*4, s));
+            XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1), s));
+            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1), s));
             if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
             if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
@@ -375,35 +386,52 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                                (uint32_t)n1, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+        // ---- reverse search (lane s2) ----
+        Scratch refine2, resrec2, plans2;
+        XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
         if (mirror) {
             if (!self) {
                 if (fast) {
-                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec.p, plans.p, refine.as<uint32_t>(),
-                                                    &ctx->d_ctr->refine_rev, true, ctx->d_ctr, s, err, &launches))) return rc;
+                    XM_CUDA_TRY(refine2.alloc((size_t)n2*4, s2));
+                    XM_CUDA_TRY(resrec2.alloc(filter_result_bytes(n2), s2));
+                    XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2), s2));
+                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec2.p, plans2.p,
+                                                    refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
+                                                    s2, err, &launches))) return rc;
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
-                                                       refine.as<uint32_t>(), (uint32_t)n2,
-                                                       &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr, s, err,
+                                                       refine2.as<uint32_t>(), (uint32_t)n2,
+                                                       &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr, s2, err,
                                                        &launches))) return rc;
                 } else {
                     if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd, nullptr,
-                                                       (uint32_t)n2, nullptr, true, false, ctx->d_ctr, s, err, &launches))) return rc;
+                                                       (uint32_t)n2, nullptr, true, false, ctx->d_ctr, s2, err, &launches))) return rc;
                 }
             } else {
                 // reverse pass skipped (qxmatch.hpp:395): rid = npos, rd = proxy_to_true(inf)
-                if ((rc = launch_fill_outputs(rid, rd, n2, linear ? dinf : dnan, s, err, &launches))) return rc;
+                if ((rc = launch_fill_outputs(rid, rd, n2, linear ? dinf : dnan, s2, err, &launches))) return rc;
             }
         }
+        XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
+        XM_CUDA_TRY(cudaEventRecord(sev[3], s2));
+        XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[3], 0));                // join
         XM_CUDA_TRY(cudaEventRecord(ev[7], s));
         XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
         XM_CUDA_TRY(cudaEventRecord(ev[8], s));
         XM_CUDA_TRY(cudaStreamSynchronize(s));
+        XM_CUDA_TRY(cudaStreamSynchronize(s2));
         st.ms_bbox = ev_ms(ev[0], ev[1]);
         st.ms_keys = ev_ms(ev[1], ev[2]);
         st.ms_sort = ev_ms(ev[2], ev[3]);
         st.ms_index = ev_ms(ev[1], ev[5]);
+        st.ms_forward = ev_ms(ev[5], ev[6]);
+        st.ms_reverse = ev_ms(ev[9], ev[7]);           // runs concurrently with the forward search
+        st.ms_search = ev_ms(ev[5], ev[8]);
     }
-    st.ms_forward = ev_ms(ev[5], ev[6]);
-    st.ms_reverse = ev_ms(ev[6], ev[7]);
+    if (P.brute_force) {
+        st.ms_forward = ev_ms(ev[5], ev[6]);
+        st.ms_reverse = ev_ms(ev[6], ev[7]);
+        st.ms_search = ev_ms(ev[5], ev[7]);
+    }
     st.ms_total = ev_ms(ev[0], ev[8]);
     st.launches = launches;
     st.evals_fwd = ctx->h_ctr->evals_fwd; st.evals_rev = ctx->h_ctr->evals_rev;
@@ -484,6 +512,8 @@ void xm_shutdown(void) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         for (auto& e : c->ev) cudaEventDestroy(e);
+        for (auto& e : c->sync_ev) cudaEventDestroy(e);
+        cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2);
         cudaFree(c->d_small); cudaFreeHost(c->h_small);
         cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr);
         cudaStreamDestroy(c->stream);
