@@ -44,7 +44,7 @@ class ClockSampler:
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.h, self.nv = gpu_index, [], None, None
+        self.idx, self.rows, self.h, self.nv, self.max_mhz = gpu_index, [], None, None, 0.0
 
     def start(self):
         try:
@@ -57,7 +57,10 @@ class ClockSampler:
             except Exception:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
             self.nv = pynvml
-            self.sample(keep=False)          # first NVML call is slow: take it before the timed region
+            # nvmlDeviceGetMaxClockInfo takes ~2.4 ms per call on this driver: read it once, outside
+            # the timed region; the per-sample queries (current clock, reasons) take microseconds
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.sample(keep=False)
         except Exception:
             self.nv = None
 
@@ -67,7 +70,7 @@ class ClockSampler:
             return
         try:
             sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            mx = self.max_mhz
             fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             rs = fn(self.h)
             if keep:
@@ -200,11 +203,10 @@ def run_gpu_arm(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    sample_at = {0, args.steps//2, args.steps - 1} if rank == 0 else set()
     for k in range(args.steps):
         out = step(True)
-        if k in sample_at:
-            sampler.sample()                # GPU still busy with this step's tail / next launch
+        if rank == 0:
+            sampler.sample()                # a few microseconds; between two steps of the timed region
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
