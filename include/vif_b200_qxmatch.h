@@ -21,6 +21,10 @@
  *     qxmatch.hpp:165-167, 609-613);
  *   - cell-binned path with `self`: rid = XM_NPOS, rd = NaN (reverse pass skipped, qxmatch.hpp:395);
  *   - `thread` is accepted and ignored (the GPU path has no host worker threads);
+ *   - EXTENSION: where the reference's bucket grid is infeasible (catalog 2 spanning RA 0..360 gives a
+ *     hull area of 0 -> 1-arcsec cells over the whole box -> ~1e12 buckets, which the reference would
+ *     try to allocate) the cell-binned call is answered by the exact spherical grid search instead:
+ *     true nth nearest neighbours, equal distances in ascending row order, i.e. the brute_force result;
  *   - there is NO CPU fallback: every entry point that computes returns XM_ERR_CUDA when no
  *     CUDA device / kernel image is usable.
  *
@@ -45,7 +49,8 @@ enum {
     XM_ERR_INVALID_ARG = 1,           /* NULL pointer, n >= 2^32-1, bad flag combination          */
     XM_ERR_NONFINITE_1 = 2,           /* "first RA and Dec coordinates contain invalid values"    */
     XM_ERR_NONFINITE_2 = 3,           /* "second RA and Dec coordinates contain invalid values"   */
-    XM_ERR_GRID_TOO_LARGE = 4,        /* nra*ndec exceeds XM_MAX_CELLS (reference would allocate it)*/
+    XM_ERR_GRID_TOO_LARGE = 4,        /* the reference's bucket grid exceeds XM_MAX_CELLS and the exact */
+                                      /* spherical search does not apply (linear mode, nth > 8)          */
     XM_ERR_CUDA = 5,                  /* CUDA runtime failure or no device: message has details   */
     XM_ERR_NO_MEMORY = 6
 };
@@ -67,7 +72,9 @@ typedef struct xm_params {
                                       /* bin with the GLOBAL box of qxmatch.hpp:232-238)           */
     uint8_t  exact_only;              /* 1: disable the filter kernels, run reference-order maths   */
                                       /* on every pair (debug / parity triage)                     */
-    uint8_t  reserved0;
+    uint8_t  exact_grid;              /* 1 (with brute_force): compute the brute_force result with the */
+                                      /* exact spherical grid search instead of all n1*n2 pairs; chosen  */
+                                      /* automatically above 4e12 pairs. Identical results.             */
     int32_t  device;                  /* CUDA ordinal; -1 = current device                         */
     int32_t  reserved1;
     double   bbox1[4];                /* ra_min, ra_max, dec_min, dec_max                          */

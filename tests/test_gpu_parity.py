@@ -151,9 +151,58 @@ def test_errors_nonfinite_and_grid():
     ra2, dec2 = G.fullsky(2, 1000)
     ra2[:4] = [0.0, 0.0, 360.0, 360.0]           # bounding box = the whole sphere: hull area 0
     dec2[:4] = [-90.0, 90.0, -90.0, 90.0]
-    with pytest.raises(QxmatchError) as e:       # 1-arcsec cells over the whole sky
-        qxmatch(ra, dec, ra2, dec2)
+    with pytest.raises(QxmatchError) as e:       # 1-arcsec cells over the whole sky;
+        qxmatch(ra, dec, ra2, dec2, nth=9)       # the exact-grid extension stops at nth = 8
     assert e.value.code == _lib.XM_ERR_GRID_TOO_LARGE
+
+
+def _sphere_cases():
+    rng = np.random.default_rng(7)
+    fs1, fs2 = G.fullsky(41, 20_000), G.fullsky(42, 18_000)
+    cap = lambda seed, n: (360.0*G.uniform(seed, 0, n), 90.0 - 4.0*np.sqrt(G.uniform(seed, 1, n)))     # polar cap
+    wrapbox = lambda seed, n: ((350.0 + 20.0*G.uniform(seed, 0, n)) % 360.0, -10 + 20*G.uniform(seed, 1, n))
+    yield "fullsky", fs1, fs2, dict()
+    yield "fullsky_nth4", fs1, fs2, dict(nth=4)
+    yield "fullsky_nth8_nomirror", (fs1[0][:3000], fs1[1][:3000]), fs2, dict(nth=8, no_mirror=True)
+    yield "north_cap", cap(43, 8000), cap(44, 9000), dict(nth=2)
+    yield "south_cap", (cap(45, 5000)[0], -cap(45, 5000)[1]), (cap(46, 5000)[0], -cap(46, 5000)[1]), dict()
+    yield "ra_wrap_box", wrapbox(47, 15_000), wrapbox(48, 15_000), dict(nth=3)
+    yield "sparse", G.fullsky(49, 3000), G.fullsky(50, 7), dict(nth=3)
+    yield "single_candidate", G.fullsky(51, 500), G.fullsky(52, 1), dict()
+    d2 = (fs2[0].copy(), fs2[1].copy()); d2[0][9000:] = d2[0][:9000]; d2[1][9000:] = d2[1][:9000]
+    yield "duplicates", (fs1[0][:8000], fs1[1][:8000]), d2, dict(nth=2)
+    yield "compact_box", G.c1(53, 20_000), G.c1(54, 20_000), dict(nth=2)
+
+
+@pytest.mark.parametrize("name,c1,c2,kw", list(_sphere_cases()), ids=[c[0] for c in _sphere_cases()])
+def test_exact_grid_equals_brute_force(oracle, name, c1, c2, kw):
+    """brute_force + exact_grid: the spherical grid search must return the brute-force result
+    (oracle = the reference's brute_force port), poles, RA wrap and ties included."""
+    exp = oracle.oracle_qxmatch(c1[0], c1[1], c2[0], c2[1], brute_force=True, thread=os.cpu_count() or 8, **kw)
+    got = qxmatch(c1[0], c1[1], c2[0], c2[1], brute_force=True, exact_grid=True, **kw)
+    assert_same_result(got, exp, RTOL, name)
+    assert got.stats["evals_fwd"] < 0.5*c1[0].size*c2[0].size or c2[0].size < 100      # it did not scan all pairs
+
+
+def test_exact_grid_self(oracle):
+    ra, dec = G.fullsky(55, 15_000)
+    exp = oracle.oracle_qxmatch(ra, dec, ra, dec, brute_force=True, self=True, nth=3, thread=os.cpu_count() or 8)
+    got = qxmatch(ra, dec, brute_force=True, exact_grid=True, nth=3)
+    assert_same_result(got, exp, RTOL, "sphere-self")
+
+
+def test_binned_call_on_full_sky_uses_exact_grid(oracle):
+    """C5-shaped: the reference's binned path cannot run on a full-sky catalog; the
+    library answers with the exact neighbours, checked against the reference's brute force."""
+    ra1, dec1 = G.fullsky(56, 30_000)
+    ra2, dec2 = G.fullsky(57, 25_000)
+    ra2[:4] = [0.0, 0.0, 360.0, 360.0]; dec2[:4] = [-90.0, 90.0, -90.0, 90.0]
+    exp = oracle.oracle_qxmatch(ra1, dec1, ra2, dec2, brute_force=True, thread=os.cpu_count() or 8)
+    got = qxmatch(ra1, dec1, ra2, dec2)                       # brute_force = False
+    assert_same_result(got, exp, RTOL, "fullsky-binned")
+    gs = qxmatch(ra2, dec2, nth=2)                            # binned self match: reverse pass skipped
+    es = oracle.oracle_qxmatch(ra2, dec2, ra2, dec2, brute_force=True, self=True, nth=2, no_mirror=True, thread=8)
+    assert np.array_equal(gs.id, es["id"]) and np.all(gs.rid == NPOS) and np.all(np.isnan(gs.rd))
 
 
 def test_sort_pairs_is_stable_and_sorted():

@@ -15,7 +15,7 @@ XM_OK, XM_ERR_INVALID_ARG, XM_ERR_NONFINITE_1, XM_ERR_NONFINITE_2, XM_ERR_GRID_T
 class XmParams(C.Structure):
     _fields_ = [("thread", u64), ("nth", u64), ("verbose", C.c_uint8), ("self", C.c_uint8),
                 ("brute_force", C.c_uint8), ("no_mirror", C.c_uint8), ("linear", C.c_uint8),
-                ("has_bbox1", C.c_uint8), ("exact_only", C.c_uint8), ("reserved0", C.c_uint8),
+                ("has_bbox1", C.c_uint8), ("exact_only", C.c_uint8), ("exact_grid", C.c_uint8),
                 ("device", i32), ("reserved1", i32), ("bbox1", f64 * 4)]
 
 

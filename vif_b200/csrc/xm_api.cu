@@ -177,6 +177,46 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+// Exact spherical grid search (xm_sphere.cu): brute-force semantics at neighbourhood-search cost.
+int32_t run_sphere(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
+                   const double* ra2, const double* dec2, uint64_t n2, bool same_cat, const double* bb1,
+                   const double* bb2, uint32_t nth, bool self, bool mirror, int sin_model, uint64_t* id,
+                   double* d, uint64_t* rid, double* rd, cudaEvent_t* ev, uint64_t* launches, Error& err) {
+    int32_t rc;
+    const double bb[4] = {fmin(bb1[0], bb2[0]), fmax(bb1[1], bb2[1]), fmin(bb1[2], bb2[2]), fmax(bb1[3], bb2[3])};
+    GridView g;
+    int wrap = 0;
+    if (!sphere_grid(bb, n2, nth, &g, &wrap))
+        return fail(err, XM_ERR_INVALID_ARG, "right ascensions span more than 360 degrees");
+    g.sin_model = sin_model;
+    ctx->last.grid.rra0 = g.rra0; ctx->last.grid.rdec0 = g.rdec0; ctx->last.grid.dra = g.dra; ctx->last.grid.ddec = g.ddec;
+    ctx->last.grid.nra = g.nra; ctx->last.grid.ndec = g.ndec; ctx->last.grid.cell_size = g.cell_size;
+    const uint32_t ncell = g.nra*g.ndec;
+    Scratch cmin;
+    XM_CUDA_TRY(cmin.alloc((size_t)g.ndec*8, s));
+    if ((rc = launch_sphere_rows(g, cmin.as<double>(), s, err, launches))) return rc;
+    SortedCat s1, s2;
+    if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, true, false, &ctx->d_ctr->index_overflow, s1, s, err,
+                          launches, nullptr, nullptr))) return rc;
+    const CatView* v2 = &s1.view;
+    if (!same_cat) {
+        if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, true, false, &ctx->d_ctr->index_overflow, s2, s, err,
+                              launches, nullptr, nullptr))) return rc;
+        v2 = &s2.view;
+    }
+    XM_CUDA_TRY(cudaEventRecord(ev[5], s));
+    if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), s1.view, *v2, self, nth, n1, id, d, false,
+                                   ctx->d_ctr, s, err, launches))) return rc;
+    XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+    if (mirror && (rc = launch_sphere_search(g, wrap, cmin.as<double>(), *v2, s1.view, self, 1u, n2, rid, rd, true,
+                                             ctx->d_ctr, s, err, launches))) return rc;
+    XM_CUDA_TRY(cudaEventRecord(ev[7], s));
+    XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
+    XM_CUDA_TRY(cudaEventRecord(ev[8], s));
+    XM_CUDA_TRY(cudaStreamSynchronize(s));
+    return XM_OK;
+}
+
 int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const double* dec1, uint64_t n1,
                         const double* ra2, const double* dec2, uint64_t n2, const xm_params& P,
                         uint64_t* id, double* d, uint64_t* rid, double* rd, bool use_bucket, Error& err) {
@@ -237,7 +277,16 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
     g.linear = linear ? 1 : 0;
     g.sin_model = sin_model;
 
-    if (P.brute_force) {
+    bool sphere_done = false;
+    if (P.brute_force && sphere_applicable(linear, (uint32_t)nth) &&
+        (P.exact_grid || (double)n1*(double)n2 > 4e12)) {
+        // ---- brute_force result through the exact spherical grid search ----
+        if ((rc = run_sphere(ctx, s, ra1, dec1, n1, ra2, dec2, n2, same_cat, bb1, bb2, (uint32_t)nth, self, mirror,
+                             sin_model, id, d, rid, rd, ev, &launches, err))) return rc;
+        sphere_done = true;
+        st.ms_bbox = ev_ms(ev[0], ev[1]);
+        st.ms_index = ev_ms(ev[1], ev[5]);
+    } else if (P.brute_force) {
         // ---- brute force (qxmatch.hpp:490-526) ----
         Scratch x1, y1, c1, x2, y2, c2;
         XM_CUDA_TRY(x1.alloc(n1*8, s)); XM_CUDA_TRY(y1.alloc(n1*8, s)); XM_CUDA_TRY(c1.alloc(n1*8, s));
@@ -304,8 +353,23 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         xm_grid G;
         grid_from_bbox(bb1, bb2, n2, nth, linear, &G);
         st.grid = G;
-        if (G.nra == 0 || G.ndec == 0 || G.nra > 0x7fffffffull || G.ndec > 0x7fffffffull ||
-            G.nra*G.ndec > XM_MAX_CELLS)
+        const bool too_large = G.nra == 0 || G.ndec == 0 || G.nra > 0x7fffffffull || G.ndec > 0x7fffffffull ||
+                               G.nra*G.ndec > XM_MAX_CELLS;
+        if (too_large && sphere_applicable(linear, (uint32_t)nth)) {
+            // The reference cannot run here (it would allocate the grid). Answer with the exact
+            // neighbours instead -- what its binned search returns wherever that search is exact.
+            if ((rc = run_sphere(ctx, s, ra1, dec1, n1, ra2, dec2, n2, same_cat, bb1, bb2, (uint32_t)nth, self,
+                                 mirror && !self, sin_model, id, d, rid, rd, ev, &launches, err))) return rc;
+            if (mirror && self) {     // binned + self: the reverse pass is skipped (qxmatch.hpp:395)
+                if ((rc = launch_fill_outputs(rid, rd, n2, dnan, s, err, &launches))) return rc;
+                XM_CUDA_TRY(cudaStreamSynchronize(s));
+            }
+            sphere_done = true;
+            st.ms_bbox = ev_ms(ev[0], ev[1]);
+            st.ms_index = ev_ms(ev[1], ev[5]);
+            goto finish;
+        }
+        if (too_large)
             return fail(err, XM_ERR_GRID_TOO_LARGE,
                         "bucket grid of %llu x %llu cells (cell size %.3g) is too large; the catalogs "
                         "span too wide a field for the cell-binned path (use brute_force)",
@@ -427,7 +491,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         st.ms_reverse = ev_ms(ev[9], ev[7]);           // runs concurrently with the forward search
         st.ms_search = ev_ms(ev[5], ev[8]);
     }
-    if (P.brute_force) {
+finish:
+    if (P.brute_force || sphere_done) {
         st.ms_forward = ev_ms(ev[5], ev[6]);
         st.ms_reverse = ev_ms(ev[6], ev[7]);
         st.ms_search = ev_ms(ev[5], ev[7]);
@@ -435,7 +500,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
     st.ms_total = ev_ms(ev[0], ev[8]);
     st.launches = launches;
     st.evals_fwd = ctx->h_ctr->evals_fwd; st.evals_rev = ctx->h_ctr->evals_rev;
-    if (P.brute_force) {                 // every pair is evaluated once per direction
+    if (P.brute_force && !sphere_done) { // every pair is evaluated once per direction
         st.evals_fwd = n1*n2 - (self ? (n1 < n2 ? n1 : n2) : 0);
         st.evals_rev = mirror ? st.evals_fwd : 0;
     }

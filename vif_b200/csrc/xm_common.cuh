@@ -133,6 +133,14 @@ int32_t launch_brute_fast(int sin_model, const void* u1, uint32_t n1, const void
                           uint64_t plane_stride, uint64_t* id_out, double* d_out, uint32_t* refine_list,
                           double* refine_thr, unsigned long long* refine_count, SearchCounters* ctr,
                           cudaStream_t s, Error& err, uint64_t* launches);
+// xm_sphere.cu: exact nth-nearest search with a wrap- and pole-aware grid (brute-force semantics)
+bool    sphere_grid(const double* bb, uint64_t n_cand, uint32_t nth, GridView* g, int* wrap);
+bool    sphere_applicable(bool linear, uint32_t nth);
+int32_t launch_sphere_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row, const CatView& src,
+                             const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
+                             uint64_t* id_out, double* d_out, bool reverse, SearchCounters* ctr,
+                             cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
                              uint64_t* launches);

@@ -1,0 +1,242 @@
+// Exact nth-nearest search on the sphere with a wrap- and pole-aware grid of our own.
+//
+// Why it exists: the reference's cell-binned path cannot run on full-sky catalogs (the hull area
+// of an RA-360 bounding box is 0 -> 1-arcsec cells -> ~10^12 buckets), and
+// its brute_force path is O(n1*n2). This kernel returns EXACTLY what brute_force returns
+// (qxmatch.hpp:490-526: the nth smallest proxies, equal proxies in ascending catalog-2 row order,
+// reverse match = smallest catalog-1 row on ties) at the cost of a neighbourhood search, so that
+// BASELINE config 5 (1e9 x 1e8 full sky) has a GPU path whose oracle is the reference's brute force.
+//
+// Grid: Dec rows of height h, RA columns of width w = 360/ncols (one width for all rows), columns
+// taken modulo ncols when the catalogs span more than half the circle (the proxy only sees
+// sin^2(dRA/2), which is 2*pi-periodic, so wrapped neighbours need no special arithmetic).
+// Search of one source: rows outward from its own (alternating above / below), inside a row the
+// cells outward from its own column (alternating east / west). A direction is abandoned as soon as
+// a rigorous lower bound of the proxy over the next cell,
+//      lb = sin^2(gap_dec/2) + sin^2(gap_ra/2) * cos(dec1) * min_row cos(dec),
+// reaches the current nth-best; rows touching a pole have min cos = 0 and are scanned whole, which
+// is what makes the result exact there. Every surviving candidate is evaluated with the
+// reference-order proxy (xm_math_exact.cuh) and inserted by (proxy, row) lexicographic order.
+#include "xm_common.cuh"
+#include "xm_math_exact.cuh"
+
+namespace xm {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kNone = 0xffffffffu;
+
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000ll); }
+
+__device__ __forceinline__ double sin2_lower(double h) {       // h >= 0
+    if (h < 0.02) { const double hh = h*h; return hh*(1.0 - hh*(1.0/3.0)); }
+    if (h <= 1.5707963267948966) { const double s = sin(h); return s*s; }
+    return 1.0;                                                 // callers clamp gaps to <= pi
+}
+
+// K best (proxy, row) pairs in lexicographic order
+template <int K>
+struct LexList {
+    double d[K];
+    uint32_t i[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { d[k] = dinf(); i[k] = kNone; }
+    }
+    __device__ __forceinline__ double kth() const { return d[K-1]; }
+    __device__ __forceinline__ void insert(double sd, uint32_t row) {
+        if (sd < d[K-1] || (sd == d[K-1] && row < i[K-1])) {
+            d[K-1] = sd; i[K-1] = row;
+#pragma unroll
+            for (int k = K-2; k >= 0; --k) {
+                if (d[k] > d[k+1] || (d[k] == d[k+1] && i[k] > i[k+1])) {
+                    const double td = d[k]; d[k] = d[k+1]; d[k+1] = td;
+                    const uint32_t ti = i[k]; i[k] = i[k+1]; i[k+1] = ti;
+                }
+            }
+        }
+    }
+};
+
+struct SphereGrid {
+    GridView g;          // rra0/rdec0/dra/ddec/nra/ndec as for any cell index (degrees)
+    int32_t  wrap;       // columns are taken modulo nra
+    const double* cmin_row;   // lower bound of cos(dec) over each row, 0 where the row touches a pole
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+sphere_search_kernel(SphereGrid sg, CatView src, CatView cand, int self_mode, uint32_t nth_eff,
+                     uint64_t plane_stride, uint64_t* __restrict__ id_out, double* __restrict__ d_out,
+                     int reverse, SearchCounters* ctr) {
+    const GridView& g = sg.g;
+    const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    unsigned long long evals = 0;
+    if (p < src.n) {
+        const Rec me = src.rec[p];
+        const double x1 = me.x, y1 = me.y, c1 = me.c < 0.0 ? 0.0 : me.c;
+        const int ncol = (int)g.nra, nrow = (int)g.ndec;
+        const int x0 = (int)(me.key/g.ndec), y0 = (int)(me.key - (uint32_t)x0*g.ndec);
+        const double wx = g.wx, wy = g.wy;           // cell widths in radians
+        LexList<K> L;
+        L.init();
+
+        bool up_done = false, dn_done = false;
+        for (int step = 0; !(up_done && dn_done); ++step) {
+            // rows in the order 0, +1, -1, +2, -2, ...
+            const int dy = step == 0 ? 0 : ((step & 1) ? (step + 1)/2 : -(step/2));
+            if (dy > 0 && up_done) continue;
+            if (dy < 0 && dn_done) continue;
+            const int row = y0 + dy;
+            if (row < 0) { dn_done = true; continue; }
+            if (row >= nrow) { up_done = true; continue; }
+            // declination gap to the row (with the binning slack), 0 for the own row
+            const double r_lo = g.oy + (double)row*wy, r_hi = r_lo + wy;
+            double gd = fmax(r_lo - y1, y1 - r_hi) - g.fzy; gd = gd > 0.0 ? gd : 0.0;
+            const double A = sin2_lower(0.5*gd)*(1.0 - 1e-9);
+            if (A >= L.kth() && dy != 0) {
+                if (dy > 0) up_done = true; else dn_done = true;
+                continue;
+            }
+            const double cm = sg.cmin_row[row];
+            const double cc = c1*cm*(1.0 - 1e-9);
+            // cells of this row outward from the own column: 0, +1, -1, +2, ...
+            const int half = sg.wrap ? ncol/2 + 1 : ncol;
+            bool e_done = false, w_done = false;
+            for (int cs = 0; !(e_done && w_done); ++cs) {
+                const int dx = cs == 0 ? 0 : ((cs & 1) ? (cs + 1)/2 : -(cs/2));
+                if (dx > 0 && e_done) continue;
+                if (dx < 0 && w_done) continue;
+                if (dx > half) { e_done = true; continue; }
+                if (dx < -half) { w_done = true; continue; }
+                int col = x0 + dx;
+                if (sg.wrap) {
+                    // a full turn brings us back to visited cells: each side covers half the circle
+                    if (dx > 0 && 2*dx > ncol) { e_done = true; continue; }
+                    if (dx < 0 && -2*dx >= ncol) { w_done = true; continue; }
+                    col %= ncol; if (col < 0) col += ncol;
+                } else {
+                    if (col < 0) { w_done = true; continue; }
+                    if (col >= ncol) { e_done = true; continue; }
+                }
+                // RA gap from the source to the cell, measured the way we walked (|dx| cells away)
+                double gr = 0.0;
+                if (dx != 0) {
+                    const double edge = dx > 0 ? (g.ox + (double)(x0 + dx)*wx) - x1 : x1 - (g.ox + (double)(x0 + dx + 1)*wx);
+                    gr = edge - g.fzx; gr = gr > 0.0 ? gr : 0.0;
+                    // sin^2(dRA/2) turns down past the antipode: a cell that reaches beyond it is
+                    // bounded by whichever of its two edges is nearer (mod 2*pi)
+                    const double two_pi = 6.283185307179586;
+                    const double far = gr + wx + 2.0*g.fzx;
+                    if (far > 3.141592653589793) { const double alt = two_pi - far; gr = fmin(gr, alt > 0.0 ? alt : 0.0); }
+                }
+                const double lb = A + sin2_lower(0.5*gr)*cc;
+                // (near the antipode the bound stops growing with |dx|: never close a side there)
+                if (lb >= L.kth() && dx != 0 && gr < 3.141592653589793 - 2.0*wx) {
+                    if (dx > 0) e_done = true; else w_done = true;
+                    continue;
+                }
+                const uint64_t ck = (uint64_t)col*g.ndec + (uint64_t)row;
+                const uint32_t qs = cand.cstart[ck], qe = cand.cstart[ck + 1];
+                for (uint32_t q = qs; q < qe; ++q) {
+                    const Rec cd = cand.rec[q];
+                    if (self_mode && cd.idx == me.idx) continue;
+                    L.insert(proxy_sph(x1, y1, me.c, cd.x, cd.y, cd.c, g.sin_model), cd.idx);
+                }
+                evals += qe - qs;
+                if (ncol == 1) { e_done = w_done = true; }
+            }
+            if (nrow == 1) { up_done = dn_done = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if ((uint32_t)k < nth_eff) {
+                id_out[(uint64_t)k*plane_stride + me.idx] = L.i[k] == kNone ? XM_NPOS : (uint64_t)L.i[k];
+                d_out[(uint64_t)k*plane_stride + me.idx] = proxy_to_true(L.d[k], false);
+            }
+        }
+    }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
+    if ((threadIdx.x & 31) == 0 && evals) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, evals);
+}
+
+__global__ void sphere_rows_kernel(GridView g, double* __restrict__ cmin) {
+    const uint32_t r = blockIdx.x*blockDim.x + threadIdx.x;
+    if (r >= g.ndec) return;
+    const double half_pi = 1.5707963267948966;
+    double lo = g.oy + (double)r*g.wy - g.fzy, hi = lo + g.wy + 2.0*g.fzy;
+    double v = 0.0;
+    if (lo > -half_pi && hi < half_pi) {
+        v = fmin(cos(lo), cos(hi))*(1.0 - 1e-12) - 1e-15;
+        if (v < 0.0) v = 0.0;
+    }
+    cmin[r] = v;
+}
+
+}  // namespace
+
+// Grid of our own for the exact search. bb = {ra_min, ra_max, dec_min, dec_max} of BOTH catalogs
+// together [deg]; n_cand = rows of the candidate catalog. Returns false when the geometry is not
+// one this path handles (RA spanning more than one turn).
+bool sphere_grid(const double* bb, uint64_t n_cand, uint32_t nth, GridView* g, int* wrap) {
+    const double pi = 3.141592653589793;
+    double ra0 = bb[0], ra1 = bb[1], de0 = bb[2], de1 = bb[3];
+    if (!(ra1 - ra0 <= 360.0)) return false;
+    if (de0 < -90.0) de0 = -90.0;
+    if (de1 > 90.0) de1 = 90.0;
+    if (!(de1 >= de0)) { de0 = -90.0; de1 = 90.0; }
+    *wrap = (ra1 - ra0) > 180.0 ? 1 : 0;
+    const double span = *wrap ? 360.0 : fmax(ra1 - ra0, 1e-9);
+    // solid angle of the box and a cell size aiming at ~8*nth candidates per cell
+    const double omega = (span*pi/180.0)*fmax(sin(de1*pi/180.0) - sin(de0*pi/180.0), 1e-12);
+    double h = sqrt(omega*8.0*(double)(nth ? nth : 1)/(double)(n_cand ? n_cand : 1))*180.0/pi;   // [deg]
+    if (h < 1.0/3600.0) h = 1.0/3600.0;
+    if (h > 10.0) h = 10.0;
+    // rows: pad by one so that every source falls strictly inside
+    double nrow_f = ceil((de1 - de0)/h) + 1.0, ncol_f = *wrap ? floor(360.0/h) : ceil(span/h) + 1.0;
+    if (ncol_f < 1.0) ncol_f = 1.0;
+    while (nrow_f*ncol_f > (double)XM_MAX_CELLS) { h *= 1.5; nrow_f = ceil((de1 - de0)/h) + 1.0; ncol_f = *wrap ? floor(360.0/h) : ceil(span/h) + 1.0; if (ncol_f < 1.0) ncol_f = 1.0; }
+    memset(g, 0, sizeof(*g));
+    g->nra = (uint32_t)ncol_f; g->ndec = (uint32_t)nrow_f;
+    g->dra = *wrap ? 360.0/ncol_f : h;
+    g->ddec = h;
+    g->rra0 = ra0;
+    g->rdec0 = de0 - 0.5*(nrow_f*h - (de1 - de0));               // centre the rows on the data
+    g->cell_size = h*3600.0;
+    const double unit = pi/180.0;
+    g->ox = g->rra0*unit; g->oy = g->rdec0*unit; g->wx = g->dra*unit; g->wy = g->ddec*unit;
+    g->fzx = 1e-12*fmax(fmax(fabs(ra0), fabs(ra1)), 360.0)*unit;
+    g->fzy = 1e-12*90.0*unit;
+    g->max_depth = g->nra > g->ndec ? g->nra : g->ndec;
+    return true;
+}
+
+int32_t launch_sphere_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err, uint64_t* launches) {
+    sphere_rows_kernel<<<(g.ndec + 255)/256, 256, 0, s>>>(g, cmin_row);
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+bool sphere_applicable(bool linear, uint32_t nth) { return !linear && nth >= 1 && nth <= 8; }
+
+int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row, const CatView& src,
+                             const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
+                             uint64_t* id_out, double* d_out, bool reverse, SearchCounters* ctr,
+                             cudaStream_t s, Error& err, uint64_t* launches) {
+    if (src.n == 0 || nth_eff == 0) return XM_OK;
+    SphereGrid sg;
+    sg.g = g; sg.wrap = wrap; sg.cmin_row = cmin_row;
+    const dim3 grid((src.n + kThreads - 1)/kThreads);
+#define XM_CASE(KK) case KK: sphere_search_kernel<KK><<<grid, kThreads, 0, s>>>(sg, src, cand, self ? 1 : 0, \
+        nth_eff, plane_stride, id_out, d_out, reverse ? 1 : 0, ctr); break;
+    switch (nth_eff) { XM_CASE(1) XM_CASE(2) XM_CASE(3) XM_CASE(4) XM_CASE(5) XM_CASE(6) XM_CASE(7) default: XM_CASE(8) }
+#undef XM_CASE
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+}  // namespace xm

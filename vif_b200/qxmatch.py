@@ -49,6 +49,7 @@ class QxmatchParams:
     device: int = -1
     bbox1: tuple = None        # (ra_min, ra_max, dec_min, dec_max) of the WHOLE catalog 1 when only
     exact_only: bool = False   # a row shard of it is passed (multi-GPU)
+    exact_grid: bool = False   # brute_force result through the exact spherical grid search
 
     def to_c(self):
         p = _lib.XmParams()
@@ -56,6 +57,7 @@ class QxmatchParams:
         p.nth = max(int(self.nth), 0)
         p.verbose, p.self, p.brute_force = int(self.verbose), int(self.self), int(self.brute_force)
         p.no_mirror, p.linear, p.exact_only = int(self.no_mirror), int(self.linear), int(self.exact_only)
+        p.exact_grid = int(self.exact_grid)
         p.device = int(self.device)
         if self.bbox1 is not None:
             p.has_bbox1 = 1
