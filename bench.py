@@ -31,9 +31,29 @@ N_FULL = 10_000_000
 SAMPLE_N = 250_000          # CPU sample: sub-box with 1/40 of the area, same source density
 
 
-def workload_desc(n1, n2):
+def workload_desc(n1, n2, config="c2"):
+    if config == "c5":
+        return ("C5: qxmatch %.0e x %.0e synthetic sources uniform on the full sky, nth=1, binned call answered by "
+                "the exact spherical grid search, reverse match (rid/rd) on" % (n1, n2))
     return ("C2: qxmatch %.0e x %.0e synthetic uniform sources over RA[0,10)xDec[-5,5) (100 deg^2), nth=1, "
             "cell-binned, reverse match (rid/rd) on" % (n1, n2))
+
+
+def gen_catalog(G, config, seed, n, dev, start=0):
+    """Rows [start, start+n) of a synthetic catalog on the device, generated in chunks."""
+    import torch
+    ra = torch.empty(n, dtype=torch.float64, device=dev)
+    dec = torch.empty(n, dtype=torch.float64, device=dev)
+    step = 50_000_000
+    for s0 in range(0, n, step):
+        m = min(step, n - s0)
+        if config == "c5":
+            a, b = G.fullsky(seed, m, xp="torch", device=dev, start=start + s0)
+        else:
+            a, b = G.c2(seed, m, xp="torch", device=dev, start=start + s0)
+        ra[s0:s0 + m] = a
+        dec[s0:s0 + m] = b
+    return ra, dec
 
 
 # ---- clocks sampling --------------------------------------------------------------------------
@@ -161,12 +181,14 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
-    n1 = n2 = args.n
+    n1 = args.n
+    n2 = args.n2 if args.n2 else (args.n // 10 if args.config == "c5" else args.n)
     lo, hi = shard_bounds(n1, world, rank)
-    ra1, dec1 = G.c2(1, hi - lo, xp="torch", device=dev, start=lo)      # this rank's rows of catalog 1
+    ra1, dec1 = gen_catalog(G, args.config, 1, hi - lo, dev, start=lo)  # this rank's rows of catalog 1
     if rank == 0:
-        ra2, dec2 = G.c2(2, n2, xp="torch", device=dev)
+        ra2, dec2 = gen_catalog(G, args.config, 2, n2, dev)
     else:
         ra2 = torch.empty(n2, dtype=torch.float64, device=dev)
         dec2 = torch.empty(n2, dtype=torch.float64, device=dev)
@@ -196,7 +218,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("XM_BENCH_NO_CLOCKS"):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(False)
@@ -219,6 +241,21 @@ def run_gpu_arm(args):
     value = n1 / (ms_step * 1e-3)
 
     # ---- end to end through the host-buffer call -------------------------------------------------
+    if args.no_e2e:
+        e2e_value, e2e_steps, h2d, d2h = None, 0, 0, 0
+        dt = torch.tensor([0.0], dtype=torch.float64, device=dev)
+    else:
+        e2e_value, e2e_steps, h2d, d2h, dt = run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params,
+                                                     dev, barrier, qxmatch, qxmatch_sharded)
+    if rank == 0:
+        emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_acc, e2e_value, e2e_steps, h2d, d2h, dt)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev, barrier, qxmatch, qxmatch_sharded):
+    import torch
+    import torch.distributed as dist
     h = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in
          (("ra1", ra1), ("dec1", dec1), ("ra2", ra2), ("dec2", dec2))}
     if world > 1:
@@ -265,9 +302,11 @@ def run_gpu_arm(args):
     dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = n1 / dt.item()
+    return n1 / dt.item(), e2e_steps, h2d, d2h, dt
 
-    if rank == 0:
+
+def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_acc, e2e_value, e2e_steps, h2d, d2h, dt):
+    if True:
         peaks, how = measured_peaks()
         ns = max(stats_acc["steps"], 1)
         # dominant kernel: the ring search (forward + reverse launches, same kernel). Algorithmic
@@ -280,7 +319,7 @@ def run_gpu_arm(args):
         achieved = (bytes_fwd + bytes_rev) / (ms_s * 1e-3) / 1e9 if ms_s > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ring_search_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == "c2" and world == 1 and n1 == N_FULL:
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
@@ -290,15 +329,16 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(n1, n2), "n1": n1, "n2": n2, "nth": 1,
+            "config": {"workload": workload_desc(n1, n2, args.config), "n1": n1, "n2": n2, "nth": 1,
                        "l2": "no flush: the 320 MB of input coordinates plus the ~0.5 GB cell index exceed the 126 MB L2",
                        "parallelism": "catalog-1 rows sharded over %d rank(s); catalog 2 NCCL-broadcast and indexed per rank; "
                                       "reverse match merged with all-reduce(min)" % world},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": dt.item() * 1e3, "steps": e2e_steps},
+            "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "ms_per_step": dt.item() * 1e3, "steps": e2e_steps} if e2e_value is not None else None),
             "gpu_launches": int(launches.item()),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ring_nn_filter_kernel (forward + reverse launches, run concurrently)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": ("sphere_search_kernel (forward + reverse launches)" if args.config == "c5" else
+                                                   "ring_nn_filter_kernel (forward + reverse launches, run concurrently)"), "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic, "peak_source": how,
                          "algorithmic_bytes_per_launch": {"forward": bytes_fwd, "reverse": bytes_rev},
@@ -308,7 +348,7 @@ def run_gpu_arm(args):
                          "stage_ms": {k: stats_acc[k] / ns for k in ("ms_total", "ms_bbox", "ms_index", "ms_search", "ms_forward", "ms_reverse")},
                          "distance_evals_per_step": stats_acc["evals"] / ns},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "c2":
             a1, b1, a2, b2, desc = cpu_sample()
             fn, kind, cores = cpu_runner()
             fn(a1[:20000], b1[:20000], a2[:20000], b2[:20000])
@@ -320,8 +360,6 @@ def run_gpu_arm(args):
             cdt = (time.perf_counter() - t0) / reps
             line["cpu_baseline"] = {"value": SAMPLE_N / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -330,9 +368,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL, help="rows per catalog (default: the full C2 workload)")
+    ap.add_argument("--rows", dest="n", type=int, default=None, help="rows of catalog 1 (default: the full workload)")
+    ap.add_argument("--rows2", dest="n2", type=int, default=None, help="rows of catalog 2 (default: n for c2, n/10 for c5)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+                    help="c2 = the headline metric's workload (default); c5 = 1e9 x 1e8 full sky (manual scaling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = 1_000_000_000 if args.config == "c5" else N_FULL
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -155,6 +155,24 @@ int32_t xm_last_stats(int32_t device, xm_stats* out);
 int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t key_bits,
                           int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
+/*
+ * Reverse-match merge for row-sharded multi-GPU runs (one exchange step; the
+ * counterpart of the reference's per-thread merge, qxmatch.hpp:478-488 / 592-603). Each rank holds
+ * (rid, rd) over ITS catalog-1 rows. The host interleaves three tiny kernels with two all-reduces:
+ *   xm_rev_merge_pack   rid -> global row id (or INT64_MAX when unmatched), key = rd (or +inf)
+ *   all-reduce(min) on a copy of key                                  -> best
+ *   xm_rev_merge_mask   rid kept only where this rank's key equals best
+ *   all-reduce(min) on rid (as int64)                                 -> smallest row among winners
+ *   xm_rev_merge_unpack rid INT64_MAX -> XM_NPOS, rd = best (or `unmatched`: NaN / inf)
+ * All pointers are device pointers on `device`; `stream` is a cudaStream_t or NULL.
+ */
+int32_t xm_rev_merge_pack(uint64_t* rid, const double* rd, uint64_t n, uint64_t row_offset, double* key,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap);
+int32_t xm_rev_merge_mask(uint64_t* rid, const double* key_local, const double* key_best, uint64_t n,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap);
+int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, uint64_t n, double unmatched,
+                            int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
 /* Host-only: entry list of ring `k` of the reference's depth_cache (qxmatch.hpp:44-128) for an
  * (nx, ny) grid, in visiting order, as the kernels enumerate it (closed form, no table). Writes up
  * to `cap` (bx, by) pairs, returns the entry count. dedupe != 0 drops the repeated axis cells. */

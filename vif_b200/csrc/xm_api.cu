@@ -735,6 +735,43 @@ int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t ke
     return rc;
 }
 
+static int32_t merge_entry(int which, uint64_t* rid, double* rd, const double* ka, const double* kb, double* key,
+                           uint64_t n, uint64_t off, double unmatched, int32_t device, void* stream,
+                           char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            int32_t r = launch_merge_step(which, (unsigned long long*)rid, rd, ka, kb, key, n, off, unmatched, s, err);
+            if (r) return r;
+            XM_CUDA_TRY(cudaStreamSynchronize(s));       // tiny kernels: keep the host-side ordering simple
+            return XM_OK;
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
+int32_t xm_rev_merge_pack(uint64_t* rid, const double* rd, uint64_t n, uint64_t row_offset, double* key,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    return merge_entry(0, rid, const_cast<double*>(rd), nullptr, nullptr, key, n, row_offset, 0.0, device, stream, errbuf, errcap);
+}
+
+int32_t xm_rev_merge_mask(uint64_t* rid, const double* key_local, const double* key_best, uint64_t n,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    return merge_entry(1, rid, nullptr, key_local, key_best, nullptr, n, 0, 0.0, device, stream, errbuf, errcap);
+}
+
+int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, uint64_t n, double unmatched,
+                            int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    return merge_entry(2, rid, rd, nullptr, key_best, nullptr, n, 0, unmatched, device, stream, errbuf, errcap);
+}
+
 uint64_t xm_ring_entries(uint32_t k, uint32_t nx, uint32_t ny, int32_t dedupe, int32_t* bx,
                          int32_t* by, uint64_t cap) {
     uint64_t n = 0;

@@ -123,7 +123,47 @@ cell_offsets_kernel(const uint32_t* __restrict__ skeys, uint32_t n, uint32_t nce
     cstart[k] = lo;
 }
 
+constexpr unsigned long long kLost = 0x7fffffffffffffffull;       // INT64_MAX: loses every min
+
+__global__ void merge_pack_kernel(unsigned long long* __restrict__ rid, const double* __restrict__ rd,
+                                  uint64_t n, unsigned long long off, double* __restrict__ key) {
+    const uint64_t j = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long r = rid[j];
+    const bool ok = r != ~0ull;
+    rid[j] = ok ? r + off : kLost;
+    key[j] = ok ? rd[j] : __longlong_as_double(0x7ff0000000000000ll);
+}
+
+__global__ void merge_mask_kernel(unsigned long long* __restrict__ rid, const double* __restrict__ kl,
+                                  const double* __restrict__ kb, uint64_t n) {
+    const uint64_t j = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (!(kl[j] == kb[j])) rid[j] = kLost;
+}
+
+__global__ void merge_unpack_kernel(unsigned long long* __restrict__ rid, double* __restrict__ rd,
+                                    const double* __restrict__ kb, uint64_t n, double unmatched) {
+    const uint64_t j = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const bool ok = rid[j] != kLost;
+    if (!ok) rid[j] = ~0ull;
+    rd[j] = ok ? kb[j] : unmatched;
+}
+
 }  // namespace
+
+int32_t launch_merge_step(int which, unsigned long long* rid, double* rd, const double* ka, const double* kb,
+                          double* key_out, uint64_t n, unsigned long long off, double unmatched,
+                          cudaStream_t s, Error& err) {
+    if (n == 0) return XM_OK;
+    const unsigned blocks = (unsigned)((n + 255)/256);
+    if (which == 0) merge_pack_kernel<<<blocks, 256, 0, s>>>(rid, rd, n, off, key_out);
+    else if (which == 1) merge_mask_kernel<<<blocks, 256, 0, s>>>(rid, ka, kb, n);
+    else merge_unpack_kernel<<<blocks, 256, 0, s>>>(rid, rd, kb, n, unmatched);
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
 
 int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
                     cudaStream_t s, Error& err, uint64_t* launches) {

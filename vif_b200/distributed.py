@@ -15,6 +15,9 @@ No collective touches the forward path. `compute` and `bbox` are injectable so t
 and merge logic is testable on CPU with the gloo backend (tests/test_distributed_gloo.py); the
 defaults are the CUDA library and there is no CPU implementation in this module.
 """
+import os
+import time
+
 import numpy as np
 
 
@@ -61,32 +64,93 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     compute = compute or _cuda_compute
     bbox = bbox or _cuda_bbox
     world = dist.get_world_size(group)
+    timing = os.environ.get("XM_DIST_TIMING") and ra1_local.is_cuda
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     if params.self:
         raise ValueError("self-match shards catalog 1 against itself: pass the full catalog as "
                          "catalog 2 and self=False with an explicit id offset instead")
     if broadcast_cat2 and world > 1:
         dist.broadcast(ra2, src=src, group=group)
         dist.broadcast(dec2, src=src, group=group)
+    mark("broadcast")
 
-    # global bounding box of catalog 1 (qxmatch.hpp:232-238)
+    # global bounding box of catalog 1 (qxmatch.hpp:232-238): one all-reduce(max) on
+    # (-ra_min, ra_max, -dec_min, dec_max)
     bb = bbox(ra1_local, dec1_local)
-    lo = torch.tensor([bb[0], bb[2]], dtype=torch.float64, device=ra1_local.device)
-    hi = torch.tensor([bb[1], bb[3]], dtype=torch.float64, device=ra1_local.device)
+    ext = torch.tensor([-bb[0], bb[1], -bb[2], bb[3]], dtype=torch.float64, device=ra1_local.device)
     if world > 1:
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-    lo, hi = lo.tolist(), hi.tolist()
-    p = QxmatchParams(**{**params.__dict__, "bbox1": (lo[0], hi[0], lo[1], hi[1])})
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+    ext = ext.tolist()
+    mark("bbox")
+    p = QxmatchParams(**{**params.__dict__, "bbox1": (-ext[0], ext[1], -ext[2], ext[3])})
 
     res = compute(ra1_local, dec1_local, ra2, dec2, p)
+    mark("compute")
     ident, d, rid, rd = res.id, res.d, res.rid, res.rd
     if p.no_mirror:
         return ident, d, rid, rd
 
-    big = torch.iinfo(torch.int64).max
     rid = torch.as_tensor(rid).view(torch.int64) if not isinstance(rid, torch.Tensor) else rid
     rd = torch.as_tensor(rd) if not isinstance(rd, torch.Tensor) else rd
-    rid = torch.where(rid < 0, torch.full_like(rid, big), rid + int(row_offset))
+    if rid.is_cuda:
+        _merge_reverse_cuda(rid, rd, int(row_offset), bool(p.linear), world, group)
+    else:
+        rid, rd = _merge_reverse_torch(rid, rd, int(row_offset), world, group)
+    mark("merge")
+    if timing and dist.get_rank(group) == 0:
+        print("[qxmatch_sharded] " + " ".join("%s=%.3fms" % (marks[k][0], 1e3*(marks[k][1] - marks[k-1][1]))
+                                              for k in range(1, len(marks))), flush=True)
+    return ident, d, rid, rd
+
+
+def _merge_reverse_cuda(rid, rd, row_offset, linear, world, group):
+    """In place, three fused kernels of the library around the two all-reduces
+    (xm_rev_merge_pack / _mask / _unpack, include/vif_b200_qxmatch.h)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    n = rid.numel()
+    dev = rid.device.index or 0
+    stream = torch.cuda.current_stream(rid.device).cuda_stream
+    err = C.create_string_buffer(512)
+    key = torch.empty_like(rd)
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+
+    # The library launches on its own (non-blocking) stream when torch's current stream is the
+    # legacy default stream (handle 0 == "NULL"), so order the steps on the host: after an
+    # all-reduce, synchronising the current stream guarantees the collective has landed.
+    cur = torch.cuda.current_stream(rid.device)
+    check(lib.xm_rev_merge_pack(rid.data_ptr(), rd.data_ptr(), n, row_offset, key.data_ptr(), dev, stream, err, 512))
+    best = key.clone()
+    if world > 1:
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    cur.synchronize()
+    check(lib.xm_rev_merge_mask(rid.data_ptr(), key.data_ptr(), best.data_ptr(), n, dev, stream, err, 512))
+    if world > 1:
+        dist.all_reduce(rid, op=dist.ReduceOp.MIN, group=group)
+    cur.synchronize()
+    unmatched = float("inf") if linear else float("nan")
+    check(lib.xm_rev_merge_unpack(rid.data_ptr(), rd.data_ptr(), best.data_ptr(), n, unmatched, dev, stream, err, 512))
+
+
+def _merge_reverse_torch(rid, rd, row_offset, world, group):
+    """Same rule with plain torch ops (CPU tensors: the gloo tests)."""
+    import torch
+    import torch.distributed as dist
+    big = torch.iinfo(torch.int64).max
+    rid = torch.where(rid < 0, torch.full_like(rid, big), rid + row_offset)
     rd_key = torch.where(torch.isnan(rd), torch.full_like(rd, float("inf")), rd)
     if world > 1:
         best = rd_key.clone()
@@ -96,4 +160,4 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
         # distances of unmatched slots stay NaN (spherical) / inf (linear) as in the reference
         rd = torch.where(rid == big, rd, best)
     rid = torch.where(rid == big, torch.full_like(rid, -1), rid)
-    return ident, d, rid, rd
+    return rid, rd
