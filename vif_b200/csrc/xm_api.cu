@@ -195,25 +195,38 @@ int32_t run_sphere(Context* ctx, cudaStream_t s, const double* ra1, const double
     Scratch cmin;
     XM_CUDA_TRY(cmin.alloc((size_t)g.ndec*8, s));
     if ((rc = launch_sphere_rows(g, cmin.as<double>(), s, err, launches))) return rc;
-    SortedCat s1, s2;
+    // two lanes, as in the cell-binned path: s = catalog-1 index + forward, s2 = catalog-2 index + reverse
+    cudaStream_t s2 = ctx->stream2;
+    cudaEvent_t* sev = ctx->sync_ev;
+    XM_CUDA_TRY(cudaEventRecord(sev[0], s));
+    XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[0], 0));
+    SortedCat s1, s2cat;
     if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, true, false, &ctx->d_ctr->index_overflow, s1, s, err,
                           launches, nullptr, nullptr))) return rc;
     const CatView* v2 = &s1.view;
     if (!same_cat) {
-        if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, true, false, &ctx->d_ctr->index_overflow, s2, s, err,
-                              launches, nullptr, nullptr))) return rc;
-        v2 = &s2.view;
+        if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, true, false, &ctx->d_ctr->index_overflow, s2cat, s2,
+                              err, launches, nullptr, nullptr))) return rc;
+        v2 = &s2cat.view;
     }
+    XM_CUDA_TRY(cudaEventRecord(sev[1], s));
+    XM_CUDA_TRY(cudaEventRecord(sev[2], s2));
+    XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[2], 0));
+    XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[1], 0));
     XM_CUDA_TRY(cudaEventRecord(ev[5], s));
     if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), s1.view, *v2, self, nth, n1, id, d, false,
                                    ctx->d_ctr, s, err, launches))) return rc;
     XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+    XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
     if (mirror && (rc = launch_sphere_search(g, wrap, cmin.as<double>(), *v2, s1.view, self, 1u, n2, rid, rd, true,
-                                             ctx->d_ctr, s, err, launches))) return rc;
-    XM_CUDA_TRY(cudaEventRecord(ev[7], s));
+                                             ctx->d_ctr, s2, err, launches))) return rc;
+    XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
+    XM_CUDA_TRY(cudaEventRecord(sev[3], s2));
+    XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[3], 0));
     XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
     XM_CUDA_TRY(cudaEventRecord(ev[8], s));
     XM_CUDA_TRY(cudaStreamSynchronize(s));
+    XM_CUDA_TRY(cudaStreamSynchronize(s2));
     return XM_OK;
 }
 
@@ -492,7 +505,11 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         st.ms_search = ev_ms(ev[5], ev[8]);
     }
 finish:
-    if (P.brute_force || sphere_done) {
+    if (sphere_done) {
+        st.ms_forward = ev_ms(ev[5], ev[6]);
+        st.ms_reverse = ev_ms(ev[9], ev[7]);           // concurrent with the forward search
+        st.ms_search = ev_ms(ev[5], ev[8]);
+    } else if (P.brute_force) {
         st.ms_forward = ev_ms(ev[5], ev[6]);
         st.ms_reverse = ev_ms(ev[6], ev[7]);
         st.ms_search = ev_ms(ev[5], ev[7]);

@@ -139,9 +139,22 @@ sphere_search_kernel(SphereGrid sg, CatView src, CatView cand, int self_mode, ui
                 }
                 const uint64_t ck = (uint64_t)col*g.ndec + (uint64_t)row;
                 const uint32_t qs = cand.cstart[ck], qe = cand.cstart[ck + 1];
+                const double kth4 = 4.0*L.kth()*(1.0 + 1e-12);
                 for (uint32_t q = qs; q < qe; ++q) {
                     const Rec cd = cand.rec[q];
                     if (self_mode && cd.idx == me.idx) continue;
+                    // Cheap rejection before the two libm-grade sines: sin^2(h) >= h^2 (1 - h^2/3) for
+                    // every h, hence 4p >= Q (1 - M/12) with Q = dy^2 + dx^2 cos cos, M = max(dx^2, dy^2)
+                    // (dx wrapped into [-pi, pi]: the proxy is 2*pi-periodic in it). A candidate whose
+                    // bound is strictly above the current nth best cannot enter the list, ties included.
+                    double dx = cd.x - x1;
+                    const double dy = cd.y - y1;
+                    if (sg.wrap) dx = dx > 3.141592653589793 ? dx - 6.283185307179586
+                                                             : (dx < -3.141592653589793 ? dx + 6.283185307179586 : dx);
+                    const double dx2 = dx*dx, dy2 = dy*dy;
+                    const double Q = fma(dx2*cd.c, c1, dy2);
+                    const double M = dx2 > dy2 ? dx2 : dy2;
+                    if (me.c >= 0.0 && cd.c >= 0.0 && Q*(1.0 - M*(1.0/12.0) - 1e-12) >= kth4) continue;
                     L.insert(proxy_sph(x1, y1, me.c, cd.x, cd.y, cd.c, g.sin_model), cd.idx);
                 }
                 evals += qe - qs;
