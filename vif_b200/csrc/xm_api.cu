@@ -78,10 +78,11 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     XM_CUDA_TRY(cudaMalloc(&c->d_ctr, sizeof(SearchCounters)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_ctr, sizeof(SearchCounters)));
     for (auto& e : c->ev) XM_CUDA_TRY(cudaEventCreate(&e));
-    // keep freed scratch in the stream-ordered pool: repeated calls then never hit cudaMalloc
+    // keep up to 8 GB of freed scratch in the stream-ordered pool: repeated calls on the benchmark
+    // sizes never hit cudaMalloc, while a 1e9-row call hands its ~80 GB back at the next sync
     cudaMemPool_t pool;
     XM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
+    uint64_t keep = 8ull << 30;
     XM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     c->sin_model = calibrate_sin_model();
     XM_CUDA_TRY(cudaSetDevice(prev));
