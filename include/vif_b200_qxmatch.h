@@ -173,6 +173,16 @@ int32_t xm_rev_merge_mask(uint64_t* rid, const double* key_local, const double* 
 int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, uint64_t n, double unmatched,
                             int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
+/*
+ * Mutual-best filter on the device (replaces xmatch_clean_best, qxmatch.hpp:641-663, while id/rid
+ * are still resident): row i of catalog 1 is kept when rid[id[i]] == i. id = rank-0 plane (n1), rid
+ * (n2). Outputs (caller-allocated, n1 elements each): id1/id2 = the kept pairs in ascending i, lost =
+ * the other rows; counts[0] = pairs, counts[1] = lost (host pointer, filled before returning).
+ */
+int32_t xm_clean_best_dev(const uint64_t* id, const uint64_t* rid, uint64_t n1, uint64_t n2,
+                          uint64_t* id1, uint64_t* id2, uint64_t* lost, uint64_t* counts,
+                          int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
 /* Host-only: entry list of ring `k` of the reference's depth_cache (qxmatch.hpp:44-128) for an
  * (nx, ny) grid, in visiting order, as the kernels enumerate it (closed form, no table). Writes up
  * to `cap` (bx, by) pairs, returns the entry count. dedupe != 0 drops the repeated axis cells. */

@@ -267,3 +267,19 @@ def test_host_and_device_entries_agree():
         assert np.array_equal(getattr(h, k), dv[k])
     for k in ("d", "rd"):
         assert np.array_equal(getattr(h, k), dv[k], equal_nan=True)
+
+
+def test_clean_best_device_matches_host():
+    """xm_clean_best_dev (qxmatch.hpp:641-663 on the device) against the numpy restatement."""
+    from vif_b200 import xmatch_clean_best
+    ra1, dec1 = G.c1(71, 50_000); ra2, dec2 = G.c1(72, 40_000)
+    host = qxmatch(ra1, dec1, ra2, dec2, nth=2)
+    hp = xmatch_clean_best(host)
+    t = [torch.from_numpy(x).cuda() for x in (ra1, dec1, ra2, dec2)]
+    dp = xmatch_clean_best(qxmatch(*t, nth=2))
+    assert np.array_equal(dp.id1.cpu().numpy().view(np.uint64), hp.id1)
+    assert np.array_equal(dp.id2.cpu().numpy().view(np.uint64), hp.id2)
+    assert np.array_equal(dp.lost.cpu().numpy().view(np.uint64), hp.lost)
+    assert hp.id1.size + hp.lost.size == ra1.size and 0 < hp.lost.size < ra1.size
+    # definition check
+    assert np.all(host.rid[hp.id2] == hp.id1)

@@ -11,6 +11,7 @@ Only what `vif::astro::qxmatch` needs lives here:
 There is no CPU implementation in this package: without the CUDA library and a GPU every compute
 entry point raises.
 """
-from .qxmatch import QxmatchParams, QxmatchRes, QxmatchError, qxmatch, last_stats, NPOS  # noqa: F401
+from .qxmatch import (QxmatchParams, QxmatchRes, QxmatchError, IdPair, qxmatch, xmatch_clean_best,  # noqa: F401
+                      last_stats, NPOS)
 
 __version__ = "0.1"

@@ -43,7 +43,7 @@ class XmStats(C.Structure):
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
 SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
-           "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack"]
+           "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
 _lib = None
 
@@ -80,6 +80,8 @@ def load():
     lib.xm_ring_entries.restype = u64
     lib.xm_ring_entries.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, i32, C.POINTER(i32),
                                     C.POINTER(i32), u64]
+    lib.xm_clean_best_dev.restype = i32
+    lib.xm_clean_best_dev.argtypes = [vp, vp, u64, u64, vp, vp, vp, up, i32, vp, C.c_char_p, u64]
     lib.xm_rev_merge_pack.restype = i32
     lib.xm_rev_merge_pack.argtypes = [vp, vp, u64, u64, vp, i32, vp, C.c_char_p, u64]
     lib.xm_rev_merge_mask.restype = i32

@@ -790,6 +790,37 @@ int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, u
     return merge_entry(2, rid, rd, nullptr, key_best, nullptr, n, 0, unmatched, device, stream, errbuf, errcap);
 }
 
+int32_t xm_clean_best_dev(const uint64_t* id, const uint64_t* rid, uint64_t n1, uint64_t n2, uint64_t* id1,
+                          uint64_t* id2, uint64_t* lost, uint64_t* counts, int32_t device, void* stream,
+                          char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = (!counts || n1 >= 0xfffffffeull || (n1 && (!id || !id1 || !id2 || !lost)) || (n2 && !rid))
+                     ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            Scratch scr, dcnt;
+            XM_CUDA_TRY(scr.alloc(clean_best_scratch_bytes((uint32_t)n1), s));
+            XM_CUDA_TRY(dcnt.alloc(2*sizeof(uint64_t), s));
+            uint64_t launches = 0;
+            int32_t r = launch_clean_best(id, rid, (uint32_t)n1, n2, id1, id2, lost, dcnt.as<uint64_t>(), scr.p, s,
+                                          err, &launches);
+            if (r) return r;
+            XM_CUDA_TRY(cudaMemcpyAsync(counts, dcnt.p, 2*sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            XM_CUDA_TRY(cudaStreamSynchronize(s));
+            return XM_OK;
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
 uint64_t xm_ring_entries(uint32_t k, uint32_t nx, uint32_t ny, int32_t dedupe, int32_t* bx,
                          int32_t* by, uint64_t cap) {
     uint64_t n = 0;

@@ -180,7 +180,52 @@ order_cells_kernel(const Rec* __restrict__ in, const uint32_t* __restrict__ csta
     }
 }
 
+// ---- mutual-best filter (xmatch_clean_best, qxmatch.hpp:641-663) ------------------------------------
+__global__ void __launch_bounds__(kThreads)
+clean_flags_kernel(const uint64_t* __restrict__ id, const uint64_t* __restrict__ rid, uint32_t n1,
+                   uint64_t n2, uint32_t* __restrict__ keep) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i > n1) return;
+    uint32_t k = 0;
+    if (i < n1) {
+        const uint64_t j = id[i];                      // rank-0 plane: nearest neighbour of row i
+        k = (j < n2 && rid[j] == (uint64_t)i) ? 1u : 0u;
+    }
+    keep[i] = k;                                       // keep[n1] = 0: the scan leaves the total there
+}
+
+__global__ void __launch_bounds__(kThreads)
+clean_compact_kernel(const uint64_t* __restrict__ id, const uint32_t* __restrict__ pos, uint32_t n1,
+                     uint64_t* __restrict__ id1, uint64_t* __restrict__ id2, uint64_t* __restrict__ lost,
+                     uint64_t* __restrict__ counts) {
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const uint32_t p = pos[i], kept = pos[i + 1] - p;
+    if (kept) { id1[p] = i; id2[p] = id[i]; }
+    else lost[i - p] = i;
+    if (i == 0) { counts[0] = pos[n1]; counts[1] = (uint64_t)n1 - pos[n1]; }
+}
+
 }  // namespace
+
+size_t clean_best_scratch_bytes(uint32_t n1) { return ((size_t)n1 + 1)*sizeof(uint32_t) + bucket_scan_aux_bytes(n1); }
+
+// id1/id2: rows of catalog 1 / 2 forming mutual best pairs (ascending row of catalog 1); lost: the
+// other rows of catalog 1; counts = {number of pairs, number lost}. scratch: clean_best_scratch_bytes.
+int32_t launch_clean_best(const uint64_t* id, const uint64_t* rid, uint32_t n1, uint64_t n2, uint64_t* id1,
+                          uint64_t* id2, uint64_t* lost, uint64_t* counts, void* scratch, cudaStream_t s,
+                          Error& err, uint64_t* launches) {
+    uint32_t* pos = (uint32_t*)scratch;
+    uint32_t* aux = pos + (size_t)n1 + 1;
+    if (n1 == 0) { XM_CUDA_TRY(cudaMemsetAsync(counts, 0, 2*sizeof(uint64_t), s)); return XM_OK; }
+    clean_flags_kernel<<<(n1 + 1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(id, rid, n1, n2, pos);
+    *launches += 1;
+    exclusive_scan(pos, n1 + 1, aux, s, launches);
+    clean_compact_kernel<<<(n1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(id, pos, n1, id1, id2, lost, counts);
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
 
 size_t bucket_scan_aux_bytes(uint32_t ncell) {
     uint64_t n = (uint64_t)ncell + 1, tot = 4;

@@ -94,6 +94,10 @@ int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, con
                             uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
                             uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
                             cudaStream_t s, Error& err, uint64_t* launches);
+size_t  clean_best_scratch_bytes(uint32_t n1);
+int32_t launch_clean_best(const uint64_t* id, const uint64_t* rid, uint32_t n1, uint64_t n2, uint64_t* id1,
+                          uint64_t* id2, uint64_t* lost, uint64_t* counts, void* scratch, cudaStream_t s,
+                          Error& err, uint64_t* launches);
 // xm_sort.cu: stable LSD radix sort, result ends in (keys, vals); tmp_* same size; scratch sized
 // by sort_scratch_bytes(n)
 size_t  sort_scratch_bytes(uint64_t n);

@@ -183,3 +183,40 @@ def _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p):
     if rc != _lib.XM_OK:
         _raise(rc, err)
     return QxmatchRes(ident, d, rid, rd, last_stats(p.device))
+
+
+@dataclass
+class IdPair:
+    """Mirror of id_pair (qxmatch.hpp:636-639)."""
+    id1: object
+    id2: object
+    lost: object
+
+
+def xmatch_clean_best(res):
+    """Mutual-best filter (qxmatch.hpp:641-663): keeps row i when rid[id[i]] == i.
+    CUDA tensors (device path results) are filtered on the device by xm_clean_best_dev while they
+    are still resident; host arrays with numpy (the reference's helper is host code too)."""
+    ident, rid = res.id, res.rid
+    if _is_torch_cuda(ident):
+        import torch
+        lib = _lib.load()
+        n1, n2 = ident.shape[1], rid.numel()
+        dev = ident.device
+        id0 = ident[0].contiguous()
+        out = [torch.empty(n1, dtype=torch.int64, device=dev) for _ in range(3)]
+        counts = (C.c_uint64 * 2)()
+        err = C.create_string_buffer(512)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = lib.xm_clean_best_dev(id0.data_ptr(), rid.data_ptr() if n2 else None, n1, n2, out[0].data_ptr(),
+                                   out[1].data_ptr(), out[2].data_ptr(), counts, dev.index or 0, None, err, 512)
+        if rc != _lib.XM_OK:
+            _raise(rc, err)
+        return IdPair(out[0][:counts[0]], out[1][:counts[0]], out[2][:counts[1]])
+    id0 = np.asarray(ident)[0]
+    rid = np.asarray(rid)
+    i = np.arange(id0.size, dtype=np.uint64)
+    ok = id0 < np.uint64(rid.size)
+    keep = np.zeros(id0.size, dtype=bool)
+    keep[ok] = rid[id0[ok]] == i[ok]
+    return IdPair(i[keep], id0[keep], i[~keep])
