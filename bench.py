@@ -346,7 +346,11 @@ def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_ac
                          "whole_path": {"bytes": whole_bytes, "GBps": whole_bytes / (ms_step * 1e-3) / 1e9,
                                         "frac": whole_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                          "stage_ms": {k: stats_acc[k] / ns for k in ("ms_total", "ms_bbox", "ms_index", "ms_search", "ms_forward", "ms_reverse")},
-                         "distance_evals_per_step": stats_acc["evals"] / ns},
+                         "distance_evals_per_step": stats_acc["evals"] / ns,
+                         # the limit that actually binds: FP64/issue work of the searches, by the
+                         # 11-flop-per-evaluation convention of SURVEY.md section 8(d); nominal peak
+                         "fp64": {"achieved_tflops": 11.0 * stats_acc["evals"] / ns / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0,
+                                  "nominal_peak_tflops": 37.2}},
         }
         if world == 1 and not args.no_cpu and args.config == "c2":
             a1, b1, a2, b2, desc = cpu_sample()
