@@ -171,7 +171,7 @@ def run_gpu_arm(args):
     from vif_b200 import catalogs as G
     from vif_b200 import qxmatch
     from vif_b200.qxmatch import QxmatchParams
-    from vif_b200.distributed import qxmatch_sharded, shard_bounds
+    from vif_b200.distributed import qxmatch_sharded, qxmatch_partitioned, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +201,9 @@ def run_gpu_arm(args):
         if world == 1:
             r = qxmatch(ra1, dec1, ra2, dec2, params=params)
             out = (r.id, r.d, r.rid, r.rd)
+        elif args.config == "c2":
+            # catalogs small enough to replicate: row blocks of BOTH catalogs per rank, no merge
+            out = qxmatch_partitioned(ra1, dec1, ra2, dec2, lo, n1, params)
         else:
             out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
         if record:
@@ -282,12 +285,18 @@ def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev
             if rank == 0:
                 ra2.copy_(h["ra2"], non_blocking=True)
                 dec2.copy_(h["dec2"], non_blocking=True)
-            i_, d_, rid_, rd_ = qxmatch_sharded(a, b, ra2, dec2, lo, params)
+            if args.config == "c2":
+                from vif_b200.distributed import qxmatch_partitioned
+                i_, d_, rid_, rd_, _ = qxmatch_partitioned(a, b, ra2, dec2, lo, n1, params)
+                o["rid"][:rid_.numel()].copy_(rid_, non_blocking=True)      # every rank returns its block
+                o["rd"][:rd_.numel()].copy_(rd_, non_blocking=True)
+            else:
+                i_, d_, rid_, rd_ = qxmatch_sharded(a, b, ra2, dec2, lo, params)
+                if rank == 0:
+                    o["rid"].copy_(rid_, non_blocking=True)
+                    o["rd"].copy_(rd_, non_blocking=True)
             o["id"].copy_(i_, non_blocking=True)
             o["d"].copy_(d_, non_blocking=True)
-            if rank == 0:
-                o["rid"].copy_(rid_, non_blocking=True)
-                o["rd"].copy_(rd_, non_blocking=True)
             torch.cuda.synchronize()
         h2d = 16 * n1 + 16 * n2
         d2h = 16 * n1 + 16 * n2
@@ -331,8 +340,12 @@ def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_ac
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_desc(n1, n2, args.config), "n1": n1, "n2": n2, "nth": 1,
                        "l2": "no flush: the 320 MB of input coordinates plus the ~0.5 GB cell index exceed the 126 MB L2",
-                       "parallelism": "catalog-1 rows sharded over %d rank(s); catalog 2 NCCL-broadcast and indexed per rank; "
-                                      "reverse match merged with all-reduce(min)" % world},
+                       "parallelism": ("1 rank" if world == 1 else
+                                       ("catalog 2 NCCL-broadcast, catalog-1 row shards NCCL-all-gathered; each of the %d ranks "
+                                        "matches its row block of catalog 1 (forward) and of catalog 2 (reverse) against the "
+                                        "whole other catalog; no merge collective" % world) if args.config == "c2" else
+                                       ("catalog-1 rows sharded over %d ranks; catalog 2 NCCL-broadcast and indexed per rank; "
+                                        "reverse match merged with all-reduce(min)" % world))},
             "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "ms_per_step": dt.item() * 1e3, "steps": e2e_steps} if e2e_value is not None else None),
             "gpu_launches": int(launches.item()),

@@ -76,8 +76,15 @@ typedef struct xm_params {
                                       /* exact spherical grid search instead of all n1*n2 pairs; chosen  */
                                       /* automatically above 4e12 pairs. Identical results.             */
     int32_t  device;                  /* CUDA ordinal; -1 = current device                         */
-    int32_t  reserved1;
+    int32_t  has_ranges;              /* 1: partitioned run (xm_qxmatch_dev, cell-binned path only): both  */
+                                      /* catalogs are passed WHOLE (they are each other's candidates) but  */
+                                      /* the forward match is computed for catalog-1 rows                  */
+                                      /* [fwd_begin, fwd_begin+fwd_count) only -> id,d hold nth*fwd_count,  */
+                                      /* and the reverse match for catalog-2 rows [rev_begin, +rev_count)   */
+                                      /* -> rid,rd hold rev_count. The reference's threaded driver splits   */
+                                      /* work the same way (chunks of i AND of j, qxmatch.hpp:422-454).    */
     double   bbox1[4];                /* ra_min, ra_max, dec_min, dec_max                          */
+    uint64_t fwd_begin, fwd_count, rev_begin, rev_count;
 } xm_params;
 
 /* Grid geometry chosen for the cell-binned path (qxmatch.hpp:232-267), reported for inspection. */

@@ -30,5 +30,23 @@ for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 1
     if rank == 0:
         print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
     ok_all &= bool(flag.item())
+# partitioned run (replicated catalogs, row blocks of both): must equal the single-GPU result
+from vif_b200.distributed import qxmatch_partitioned
+for name, n1, n2 in (("partitioned", 300_001, 250_003), ("partitioned_even", 200_000, 100_000)):
+    full1 = G.c2(1, n1, xp="torch", device=dev)
+    full2 = G.c2(2, n2, xp="torch", device=dev)
+    lo, hi = shard_bounds(n1, world, rank)
+    ra2 = full2[0].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    dec2 = full2[1].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    ident, d, rid, rd, (lo2, hi2) = qxmatch_partitioned(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2,
+                                                       dec2, lo, n1, QxmatchParams(device=local))
+    ref = qxmatch(full1[0], full1[1], full2[0], full2[1], device=local)
+    ok = torch.equal(ident, ref.id[:, lo:hi]) and torch.equal(d, ref.d[:, lo:hi]) and \
+        torch.equal(rid, ref.rid[lo2:hi2]) and torch.equal(rd, ref.rd[lo2:hi2])
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
+    ok_all &= bool(flag.item())
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)

@@ -16,7 +16,8 @@ class XmParams(C.Structure):
     _fields_ = [("thread", u64), ("nth", u64), ("verbose", C.c_uint8), ("self", C.c_uint8),
                 ("brute_force", C.c_uint8), ("no_mirror", C.c_uint8), ("linear", C.c_uint8),
                 ("has_bbox1", C.c_uint8), ("exact_only", C.c_uint8), ("exact_grid", C.c_uint8),
-                ("device", i32), ("reserved1", i32), ("bbox1", f64 * 4)]
+                ("device", i32), ("has_ranges", i32), ("bbox1", f64 * 4),
+                ("fwd_begin", u64), ("fwd_count", u64), ("rev_begin", u64), ("rev_count", u64)]
 
 
 class XmGrid(C.Structure):

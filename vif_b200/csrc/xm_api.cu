@@ -250,13 +250,23 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         return fail(err, XM_ERR_INVALID_ARG, "catalogs of 2^32-2 rows or more are not supported");
     if (nth > 0xffffffffull) return fail(err, XM_ERR_INVALID_ARG, "nth is too large");
 
+    // partitioned run: outputs cover row ranges of the (whole) catalogs
+    const bool ranged = P.has_ranges != 0;
+    if (ranged) {
+        if (P.brute_force || P.self || P.linear)
+            return fail(err, XM_ERR_INVALID_ARG, "row ranges are only supported by the spherical cell-binned path without self");
+        if (P.fwd_begin + P.fwd_count > n1 || P.rev_begin + P.rev_count > n2)
+            return fail(err, XM_ERR_INVALID_ARG, "row range outside the catalog");
+    }
+    const uint64_t n1o = ranged ? P.fwd_count : n1, n2o = ranged ? P.rev_count : n2;   // rows the outputs cover
+
     cudaEvent_t* ev = ctx->ev;
     XM_CUDA_TRY(cudaEventRecord(ev[0], s));
 
     // qxmatch.hpp:157-167: outputs start as npos / inf and an empty catalog returns them as is
     if (n1 == 0 || n2 == 0) {
-        if ((rc = launch_fill_outputs(id, d, nth*n1, dinf, s, err, &launches))) return rc;
-        if (mirror && (rc = launch_fill_outputs(rid, rd, n2, dinf, s, err, &launches))) return rc;
+        if ((rc = launch_fill_outputs(id, d, nth*n1o, dinf, s, err, &launches))) return rc;
+        if (mirror && (rc = launch_fill_outputs(rid, rd, n2o, dinf, s, err, &launches))) return rc;
         XM_CUDA_TRY(cudaStreamSynchronize(s));
         st.launches = launches;
         return XM_OK;
@@ -369,6 +379,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         st.grid = G;
         const bool too_large = G.nra == 0 || G.ndec == 0 || G.nra > 0x7fffffffull || G.ndec > 0x7fffffffull ||
                                G.nra*G.ndec > XM_MAX_CELLS;
+        if (too_large && ranged)
+            return fail(err, XM_ERR_GRID_TOO_LARGE, "row ranges are not supported where the reference's bucket grid is infeasible");
         if (too_large && sphere_applicable(linear, (uint32_t)nth)) {
             // The reference cannot run here (it would allocate the grid). Answer with the exact
             // neighbours instead -- what its binned search returns wherever that search is exact.
@@ -439,6 +451,19 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                   &ctx->d_ctr->index_overflow, s2cat, s2, err, &launches, nullptr, nullptr))) return rc;
             v2 = &s2cat.view;
         }
+        // partitioned run: the searched rows are blocks of the catalogs, indexed on their own; the
+        // whole catalogs stay the candidates. Block records carry block-local rows, so results land
+        // at [0, count) of the (block-sized) outputs; rid values come from the whole catalog 1.
+        SortedCat blk1, blk2;
+        const CatView* srcF = &s1.view;
+        const CatView* srcR = v2;
+        if (ranged) {
+            if ((rc = build_index(ra1 + P.fwd_begin, dec1 + P.fwd_begin, (uint32_t)P.fwd_count, g, ncell, use_bucket,
+                                  !unordered, &ctx->d_ctr->index_overflow, blk1, s, err, &launches, nullptr, nullptr))) return rc;
+            if ((rc = build_index(ra2 + P.rev_begin, dec2 + P.rev_begin, (uint32_t)P.rev_count, g, ncell, use_bucket,
+                                  !unordered, &ctx->d_ctr->index_overflow, blk2, s2, err, &launches, nullptr, nullptr))) return rc;
+            srcF = &blk1.view; srcR = &blk2.view;
+        }
         XM_CUDA_TRY(cudaEventRecord(sev[1], s));                       // index of catalog 1 ready
         XM_CUDA_TRY(cudaEventRecord(sev[2], s2));                      // index of catalog 2 ready
         XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[2], 0));
@@ -446,53 +471,54 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         XM_CUDA_TRY(cudaEventRecord(ev[5], s));
 
         if (nth_eff < nth) {
-            if ((rc = launch_fill_outputs(id, d, nth*n1, linear ? dinf : dnan, s, err, &launches))) return rc;
+            if ((rc = launch_fill_outputs(id, d, nth*n1o, linear ? dinf : dnan, s, err, &launches))) return rc;
         }
         // ---- forward search (lane s) ----
         Scratch refine, resrec, plans;
-        if (fast && nth_eff == 1) {
-            XM_CUDA_TRY(refine.alloc((size_t)n1*4, s));
-            XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1), s));
-            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1), s));
-            if ((rc = launch_ring_nn_filter(g, s1.view, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
+        if (srcF->n == 0) {
+            // empty block: nothing to match
+        } else if (fast && nth_eff == 1) {
+            XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
+            XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1o), s));
+            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
+            if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
                                             &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
-            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, 1u, n1, id, d, refine.as<uint32_t>(),
-                                               (uint32_t)n1, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
+            if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
+                                               (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
                                                err, &launches))) return rc;
         } else {
-            if ((rc = launch_ring_search_exact(g, s1.view, *v2, self_mode, nth_eff, n1, id, d, nullptr,
-                                               (uint32_t)n1, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
+            if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, nth_eff, n1o, id, d, nullptr,
+                                               (uint32_t)n1o, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
         // ---- reverse search (lane s2) ----
         Scratch refine2, resrec2, plans2;
         XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
-        if (mirror) {
+        if (mirror && n2o) {
             if (!self) {
                 if (fast) {
-                    XM_CUDA_TRY(refine2.alloc((size_t)n2*4, s2));
-                    XM_CUDA_TRY(resrec2.alloc(filter_result_bytes(n2), s2));
-                    XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2), s2));
-                    if ((rc = launch_ring_nn_filter(g, *v2, s1.view, false, rid, rd, resrec2.p, plans2.p,
+                    XM_CUDA_TRY(refine2.alloc((size_t)n2o*4, s2));
+                    XM_CUDA_TRY(resrec2.alloc(filter_result_bytes(n2o), s2));
+                    XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
+                    if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,
                                                     refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
                                                     s2, err, &launches))) return rc;
-                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd,
-                                                       refine2.as<uint32_t>(), (uint32_t)n2,
+                    if ((rc = launch_ring_search_exact(g, *srcR, s1.view, 0, 1u, n2o, rid, rd,
+                                                       refine2.as<uint32_t>(), (uint32_t)n2o,
                                                        &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr, s2, err,
                                                        &launches))) return rc;
                 } else {
-                    if ((rc = launch_ring_search_exact(g, *v2, s1.view, 0, 1u, n2, rid, rd, nullptr,
-                                                       (uint32_t)n2, nullptr, true, false, ctx->d_ctr, s2, err, &launches))) return rc;
+                    if ((rc = launch_ring_search_exact(g, *srcR, s1.view, 0, 1u, n2o, rid, rd, nullptr,
+                                                       (uint32_t)n2o, nullptr, true, false, ctx->d_ctr, s2, err, &launches))) return rc;
                 }
             } else {
                 // reverse pass skipped (qxmatch.hpp:395): rid = npos, rd = proxy_to_true(inf)
-                if ((rc = launch_fill_outputs(rid, rd, n2, linear ? dinf : dnan, s2, err, &launches))) return rc;
+                if ((rc = launch_fill_outputs(rid, rd, n2o, linear ? dinf : dnan, s2, err, &launches))) return rc;
             }
         }
         XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
         XM_CUDA_TRY(cudaEventRecord(sev[3], s2));
         XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[3], 0));                // join
-        XM_CUDA_TRY(cudaEventRecord(ev[7], s));
         XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
         XM_CUDA_TRY(cudaEventRecord(ev[8], s));
         XM_CUDA_TRY(cudaStreamSynchronize(s));
@@ -634,6 +660,7 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
                        double* d, uint64_t* rid, double* rd, char* errbuf, uint64_t errcap) {
     Error err;
     int32_t rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
+    if (!rc && params->has_ranges) rc = fail(err, XM_ERR_INVALID_ARG, "row ranges need the device entry point (xm_qxmatch_dev)");
     Context* ctx = nullptr;
     if (!rc) rc = get_context(params->device, &ctx, err);
     if (rc) { copy_err(err, errbuf, errcap); return rc; }

@@ -110,6 +110,59 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     return ident, d, rid, rd
 
 
+def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, params, group=None, src=0,
+                        broadcast_cat2=True):
+    """Partitioned run for catalogs small enough to replicate (the benchmark's 1e7 x 1e7): the
+    reference's threaded driver gives every thread a chunk of catalog-1 rows for the forward match
+    AND a chunk of catalog-2 rows for the reverse match over shared buckets (qxmatch.hpp:422-454);
+    here every rank gets the same two chunks over replicated catalogs.
+
+      1. catalog 2: NCCL broadcast from `src`; catalog 1: NCCL all-gather of the row shards;
+      2. every rank indexes both whole catalogs (they are each other's candidates) and its two row
+         blocks, then matches block against whole catalog (xm_params.has_ranges);
+      3. no collective afterwards: id/d cover this rank's catalog-1 rows, rid/rd this rank's
+         catalog-2 rows [shard_bounds(n2, world, rank)), with GLOBAL row ids.
+
+    Compared with qxmatch_sharded this trades the reverse search over every catalog-2 row plus two
+    all-reduces for one all-gather of catalog 1 -- the better deal while catalog 1 is small; for
+    1e9-row catalogs qxmatch_sharded (no replication of catalog 1) is the one to use.
+    Returns (id, d, rid, rd, (rev_begin, rev_end)).
+    """
+    import torch
+    import torch.distributed as dist
+    from .qxmatch import QxmatchParams, qxmatch
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if broadcast_cat2 and world > 1:
+        dist.broadcast(ra2, src=src, group=group)
+        dist.broadcast(dec2, src=src, group=group)
+    n_loc = ra1_local.numel()
+    if world > 1:
+        bounds = [shard_bounds(n1_total, world, r) for r in range(world)]
+        if bounds[rank] != (int(row_offset), int(row_offset) + n_loc):
+            raise ValueError("qxmatch_partitioned expects the row blocks of shard_bounds()")
+        mx = max(hi - lo for lo, hi in bounds)
+        even = all(hi - lo == mx for lo, hi in bounds)
+        send = torch.stack((ra1_local, dec1_local)) if n_loc == mx else \
+            torch.nn.functional.pad(torch.stack((ra1_local, dec1_local)), (0, mx - n_loc))
+        buf = torch.empty((world, 2, mx), dtype=torch.float64, device=ra1_local.device)
+        dist.all_gather_into_tensor(buf, send.contiguous(), group=group)
+        if even:
+            ra1 = buf[:, 0, :].reshape(-1)
+            dec1 = buf[:, 1, :].reshape(-1)
+        else:
+            ra1 = torch.cat([buf[r, 0, :hi - lo] for r, (lo, hi) in enumerate(bounds)])
+            dec1 = torch.cat([buf[r, 1, :hi - lo] for r, (lo, hi) in enumerate(bounds)])
+        ra1, dec1 = ra1.contiguous(), dec1.contiguous()
+    else:
+        ra1, dec1 = ra1_local, dec1_local
+    lo2, hi2 = shard_bounds(ra2.numel(), world, rank)
+    p = QxmatchParams(**{**params.__dict__, "fwd_range": (int(row_offset), n_loc), "rev_range": (lo2, hi2 - lo2)})
+    res = qxmatch(ra1, dec1, ra2, dec2, params=p)
+    return res.id, res.d, res.rid, res.rd, (lo2, hi2)
+
+
 def _merge_reverse_cuda(rid, rd, row_offset, linear, world, group):
     """In place, three fused kernels of the library around the two all-reduces
     (xm_rev_merge_pack / _mask / _unpack, include/vif_b200_qxmatch.h)."""

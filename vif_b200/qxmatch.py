@@ -50,6 +50,8 @@ class QxmatchParams:
     bbox1: tuple = None        # (ra_min, ra_max, dec_min, dec_max) of the WHOLE catalog 1 when only
     exact_only: bool = False   # a row shard of it is passed (multi-GPU)
     exact_grid: bool = False   # brute_force result through the exact spherical grid search
+    fwd_range: tuple = None    # (begin, count) of catalog-1 rows to match   } partitioned runs: both catalogs
+    rev_range: tuple = None    # (begin, count) of catalog-2 rows to reverse  } whole, device path only
 
     def to_c(self):
         p = _lib.XmParams()
@@ -59,6 +61,10 @@ class QxmatchParams:
         p.no_mirror, p.linear, p.exact_only = int(self.no_mirror), int(self.linear), int(self.exact_only)
         p.exact_grid = int(self.exact_grid)
         p.device = int(self.device)
+        if self.fwd_range is not None or self.rev_range is not None:
+            p.has_ranges = 1
+            p.fwd_begin, p.fwd_count = (int(v) for v in (self.fwd_range or (0, 0)))
+            p.rev_begin, p.rev_count = (int(v) for v in (self.rev_range or (0, 0)))
         if self.bbox1 is not None:
             p.has_bbox1 = 1
             for k in range(4):
@@ -167,10 +173,13 @@ def _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p):
     dev = ra1.device
     n1, n2 = ra1.numel(), ra2.numel()
     nth = max(int(p.nth), 1)
-    ident = torch.empty((nth, n1), dtype=torch.int64, device=dev)
-    d = torch.empty((nth, n1), dtype=torch.float64, device=dev)
-    rid = torch.empty(0 if p.no_mirror else n2, dtype=torch.int64, device=dev)
-    rd = torch.empty(0 if p.no_mirror else n2, dtype=torch.float64, device=dev)
+    ranged = p.fwd_range is not None or p.rev_range is not None
+    n1o = int((p.fwd_range or (0, 0))[1]) if ranged else n1          # rows the outputs cover
+    n2o = int((p.rev_range or (0, 0))[1]) if ranged else n2
+    ident = torch.empty((nth, n1o), dtype=torch.int64, device=dev)
+    d = torch.empty((nth, n1o), dtype=torch.float64, device=dev)
+    rid = torch.empty(0 if p.no_mirror else n2o, dtype=torch.int64, device=dev)
+    rd = torch.empty(0 if p.no_mirror else n2o, dtype=torch.float64, device=dev)
     p.device = dev.index if dev.index is not None else torch.cuda.current_device()
     cp = p.to_c()
     err = C.create_string_buffer(1024)
