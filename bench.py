@@ -32,6 +32,9 @@ SAMPLE_N = 250_000          # CPU sample: sub-box with 1/40 of the area, same so
 
 
 def workload_desc(n1, n2, config="c2"):
+    if config == "c3":
+        return ("C3: self match (self=true) nth=5 on a %.0e-source clustered (Soneira-Peebles) synthetic catalog over "
+                "RA[0,10]xDec[-5,5], cell-binned" % n1)
     if config == "c5":
         return ("C5: qxmatch %.0e x %.0e synthetic sources uniform on the full sky, nth=1, binned call answered by "
                 "the exact spherical grid search, reverse match (rid/rd) on" % (n1, n2))
@@ -186,19 +189,33 @@ def run_gpu_arm(args):
     n1 = args.n
     n2 = args.n2 if args.n2 else (args.n // 10 if args.config == "c5" else args.n)
     lo, hi = shard_bounds(n1, world, rank)
-    ra1, dec1 = gen_catalog(G, args.config, 1, hi - lo, dev, start=lo)  # this rank's rows of catalog 1
-    if rank == 0:
+    if args.config == "c3":
+        levels = len(str(n1)) - 1
+        assert 10 ** levels == n1, "c3 needs a power of ten"
+        fra, fdec = G.c3_clustered(3, levels, xp="torch", device=dev)      # prefix-indexed generator: whole, then slice
+        ra1, dec1 = fra[lo:hi].clone(), fdec[lo:hi].clone()
+        del fra, fdec
+        torch.cuda.empty_cache()
+        ra2, dec2 = ra1, dec1
+        n2 = n1
+    else:
+        ra1, dec1 = gen_catalog(G, args.config, 1, hi - lo, dev, start=lo)  # this rank's rows of catalog 1
+    if args.config == "c3":
+        pass
+    elif rank == 0:
         ra2, dec2 = gen_catalog(G, args.config, 2, n2, dev)
     else:
         ra2 = torch.empty(n2, dtype=torch.float64, device=dev)
         dec2 = torch.empty(n2, dtype=torch.float64, device=dev)
-    params = QxmatchParams(nth=1, device=local)
+    params = QxmatchParams(nth=5 if args.config == "c3" else 1, device=local)
     stats_acc = {"ms_forward": 0.0, "ms_reverse": 0.0, "ms_search": 0.0, "ms_total": 0.0, "ms_index": 0.0,
                  "ms_bbox": 0.0, "launches": 0, "evals": 0, "steps": 0}
 
     def step(record):
         from vif_b200.qxmatch import last_stats
-        if world == 1:
+        if args.config == "c3":
+            out = qxmatch_partitioned(ra1, dec1, None, None, lo, n1, params, self_match=True)
+        elif world == 1:
             r = qxmatch(ra1, dec1, ra2, dec2, params=params)
             out = (r.id, r.d, r.rid, r.rd)
         elif args.config == "c2":
@@ -387,13 +404,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", dest="n", type=int, default=None, help="rows of catalog 1 (default: the full workload)")
     ap.add_argument("--rows2", dest="n2", type=int, default=None, help="rows of catalog 2 (default: n for c2, n/10 for c5)")
-    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2 = the headline metric's workload (default); c5 = 1e9 x 1e8 full sky (manual scaling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.n is None:
-        args.n = 1_000_000_000 if args.config == "c5" else N_FULL
+        args.n = {"c5": 1_000_000_000, "c3": 100_000_000}.get(args.config, N_FULL)
+    if args.config == "c3":
+        args.no_e2e = True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

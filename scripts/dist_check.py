@@ -48,5 +48,18 @@ for name, n1, n2 in (("partitioned", 300_001, 250_003), ("partitioned_even", 200
     if rank == 0:
         print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
     ok_all &= bool(flag.item())
+# partitioned self match, nth=5, clustered (C3-shaped)
+ra, dec = G.c3_clustered(3, 5, xp="torch", device=dev)
+n = ra.numel()
+lo, hi = shard_bounds(n, world, rank)
+ident, d, _, _, _ = qxmatch_partitioned(ra[lo:hi].contiguous(), dec[lo:hi].contiguous(), None, None, lo, n,
+                                        QxmatchParams(device=local, nth=5), self_match=True)
+ref = qxmatch(ra, dec, nth=5, device=local)
+ok = torch.equal(ident, ref.id[:, lo:hi]) and torch.equal(d.nan_to_num(-1.0), ref.d[:, lo:hi].nan_to_num(-1.0))
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(("OK  " if flag.item() else "FAIL"), "partitioned_self_nth5", "world", world, flush=True)
+ok_all &= bool(flag.item())
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)

@@ -136,7 +136,9 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
     XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
     XM_CUDA_TRY(out.cell.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
     int32_t rc;
-    if (use_bucket) {
+    if (n == 0) {                     // empty block of a partitioned run: every cell is empty
+        XM_CUDA_TRY(cudaMemsetAsync(out.cell.p, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
+    } else if (use_bucket) {
         Scratch tmp, rank, aux;
         if (order_cells) XM_CUDA_TRY(tmp.alloc((size_t)n*sizeof(Rec), s));
         XM_CUDA_TRY(rank.alloc((size_t)n*sizeof(uint32_t), s));
@@ -253,8 +255,10 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
     // partitioned run: outputs cover row ranges of the (whole) catalogs
     const bool ranged = P.has_ranges != 0;
     if (ranged) {
-        if (P.brute_force || P.self || P.linear)
-            return fail(err, XM_ERR_INVALID_ARG, "row ranges are only supported by the spherical cell-binned path without self");
+        if (P.brute_force || P.linear)
+            return fail(err, XM_ERR_INVALID_ARG, "row ranges are only supported by the spherical cell-binned path");
+        if (P.self && !(ra1 == ra2 && dec1 == dec2 && n1 == n2))
+            return fail(err, XM_ERR_INVALID_ARG, "row ranges with self need catalog 2 to be catalog 1 (same pointers)");
         if (P.fwd_begin + P.fwd_count > n1 || P.rev_begin + P.rev_count > n2)
             return fail(err, XM_ERR_INVALID_ARG, "row range outside the catalog");
     }
@@ -428,7 +432,10 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
 
         // qxmatch.hpp:383-387: nth is lowered to n2 after allocation; planes >= n2 keep npos / NaN
         const uint32_t nth_eff = (uint32_t)(n2 < nth ? n2 : nth);
-        const int self_mode = self ? (same_cat ? 1 : 2) : 0;
+        // partitioned self match: the searched block is indexed on its own, so "itself" is told by
+        // the original row (block row + block offset), not by the slot
+        const int self_mode = self ? ((same_cat && !ranged) ? 1 : 2) : 0;
+        g.self_off = (self && ranged) ? (uint32_t)P.fwd_begin : 0u;
         // nth = 1 on small cells away from the poles: filter kernel first, exact kernel only on
         // the rows it flags (list length stays on the device: no host round trip)
         const bool fast = !P.exact_only && fast_path_applicable(g) && self_mode != 2;

@@ -45,6 +45,7 @@ struct GridView {
     uint32_t max_depth;       // max(nra, ndec): depth_cache::size(), qxmatch.hpp:85-87
     int32_t  linear;
     int32_t  sin_model;       // 1: glibc __sin_fma Taylor branch, 2: non-FMA build of the same
+    uint32_t self_off;        // partitioned self match: source row r is candidate row r + self_off
 };
 
 struct SearchCounters {       // device counters, zeroed per call

@@ -182,7 +182,7 @@ __device__ __forceinline__ void ring_search_row(const GridView& g, const CatView
                 // catalogs share one index (1), same original row otherwise (2)
                 if (self_mode == 1 && q == p) continue;
                 const Rec cd = cand.rec[q];
-                if (self_mode == 2 && cd.idx == me.idx) continue;
+                if (self_mode == 2 && cd.idx == me.idx + g.self_off) continue;
                 const double sd = LINEAR ? proxy_lin(x1, y1, cd.x, cd.y)
                                          : proxy_sph(x1, y1, c1, cd.x, cd.y, cd.c, g.sin_model);
                 ++evals;

@@ -111,7 +111,7 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
 
 
 def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, params, group=None, src=0,
-                        broadcast_cat2=True):
+                        broadcast_cat2=True, self_match=False):
     """Partitioned run for catalogs small enough to replicate (the benchmark's 1e7 x 1e7): the
     reference's threaded driver gives every thread a chunk of catalog-1 rows for the forward match
     AND a chunk of catalog-2 rows for the reverse match over shared buckets (qxmatch.hpp:422-454);
@@ -126,15 +126,19 @@ def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, 
     Compared with qxmatch_sharded this trades the reverse search over every catalog-2 row plus two
     all-reduces for one all-gather of catalog 1 -- the better deal while catalog 1 is small; for
     1e9-row catalogs qxmatch_sharded (no replication of catalog 1) is the one to use.
+    self_match=True: one catalog matched against itself (ra2/dec2 ignored): the row shards are
+    all-gathered, every rank matches its block against the whole catalog (C3: near-linear scaling,
+    the search dominates the replicated index build). The binned self match has no reverse pass.
     Returns (id, d, rid, rd, (rev_begin, rev_end)).
     """
     import torch
     import torch.distributed as dist
     from .qxmatch import QxmatchParams, qxmatch
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    if broadcast_cat2 and world > 1:
+    live = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if live else 1
+    rank = dist.get_rank(group) if live else 0
+    if broadcast_cat2 and world > 1 and not self_match:
         dist.broadcast(ra2, src=src, group=group)
         dist.broadcast(dec2, src=src, group=group)
     n_loc = ra1_local.numel()
@@ -157,6 +161,11 @@ def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, 
         ra1, dec1 = ra1.contiguous(), dec1.contiguous()
     else:
         ra1, dec1 = ra1_local, dec1_local
+    if self_match:
+        p = QxmatchParams(**{**params.__dict__, "self": True, "no_mirror": True,
+                             "fwd_range": (int(row_offset), n_loc), "rev_range": (0, 0)})
+        res = qxmatch(ra1, dec1, ra1, dec1, params=p)
+        return res.id, res.d, res.rid, res.rd, (0, 0)
     lo2, hi2 = shard_bounds(ra2.numel(), world, rank)
     p = QxmatchParams(**{**params.__dict__, "fwd_range": (int(row_offset), n_loc), "rev_range": (lo2, hi2 - lo2)})
     res = qxmatch(ra1, dec1, ra2, dec2, params=p)
