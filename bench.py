@@ -213,8 +213,11 @@ def run_gpu_arm(args):
 
     def step(record):
         from vif_b200.qxmatch import last_stats
-        if args.config == "c3":
+        if args.config == "c3" and world > 1:
             out = qxmatch_partitioned(ra1, dec1, None, None, lo, n1, params, self_match=True)
+        elif args.config == "c3":
+            r = qxmatch(ra1, dec1, params=params)           # one-catalog overload = self match
+            out = (r.id, r.d, r.rid, r.rd)
         elif world == 1:
             r = qxmatch(ra1, dec1, ra2, dec2, params=params)
             out = (r.id, r.d, r.rid, r.rd)
