@@ -130,6 +130,12 @@ int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1
                            uint64_t* id_out, double* d_out, const uint32_t* rows, uint32_t nrows,
                            bool reverse, SearchCounters* ctr, cudaStream_t s, Error& err,
                            uint64_t* launches);
+// xm_search_topk.cu: nth = 2..8 filter kernel (multiset rule of the ring table), forward only
+bool    topk_filter_applicable(uint32_t nth_eff);
+int32_t launch_ring_topk_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
+                                uint32_t nth_eff, uint64_t plane_stride, uint64_t* id_out, double* d_out,
+                                uint32_t* refine_list, unsigned long long* refine_count, SearchCounters* ctr,
+                                cudaStream_t s, Error& err, uint64_t* launches);
 // xm_brute_fast.cu: dot-product filter + exact refine for brute_force (spherical, nth <= 4)
 size_t  brute_uvec_bytes(uint64_t n);
 bool    brute_fast_applicable(bool linear, uint32_t nth);

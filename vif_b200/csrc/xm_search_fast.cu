@@ -22,36 +22,16 @@
 // staged in shared memory by the TMA engine, ring-1 work redistributed over the CTA).
 #include "xm_common.cuh"
 #include "xm_math_exact.cuh"
+#include "xm_filter_common.cuh"
 
 namespace xm {
 
 namespace {
 
+using namespace filt;
+
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000ll); }
-
-// 5x5 block offsets, nearest first: 4 sides, 4 corners, 16 outer cells
-__constant__ int8_t c_bx[24] = {0, 1, 0, -1,   1, -1, -1, 1,
-                                0, 1, 2, 2, 2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1};
-__constant__ int8_t c_by[24] = {1, 0, -1, 0,   1, 1, -1, -1,
-                                2, 2, 2, 1, 0, -1, -2, -2, -2, -2, -2, -1, 0, 1, 2, 2};
-
-__device__ __forceinline__ Rec load_rec(const Rec* p) {
-    Rec r;
-    unsigned long long w;
-    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(r.x), "=d"(r.y), "=d"(r.c), "=l"(w) : "l"(p));
-    r.idx = (uint32_t)w;
-    r.key = (uint32_t)(w >> 32);
-    return r;
-}
-
-// Running state of one source. Q >= 0, so the high 32 bits of its IEEE pattern are a monotone
-// 21-bit-mantissa image of it: the loop tracks the smallest and second smallest HIGH WORDS with
-// native 32-bit integer min/max (FP64 min/max are multi-instruction selects on sm_100) and the slot
-// of the smallest. Two metrics with different high words are strictly ordered; metrics sharing a
-// high word (within 2^-20 of each other) are told apart by the exact kernel.
 // result of one source, padded to a DRAM sector; unpack_results_kernel splits it into id[] / d[]
 struct __align__(32) ResRec { uint64_t id; double d; uint64_t pad0, pad1; };
 
@@ -63,14 +43,6 @@ struct Best {
     int32_t h1, h2;
     uint32_t slot;
 };
-
-constexpr int32_t kInfHi = 0x7ff00000;
-
-// smallest / largest double whose high word is h
-__device__ __forceinline__ double hi_floor(int32_t h) { return __hiloint2double(h, 0); }
-__device__ __forceinline__ double hi_ceil(int32_t h) {
-    return h >= kInfHi ? __hiloint2double(kInfHi, 0) : __hiloint2double(h + 1, 0);
-}
 
 template <bool SELF>
 __device__ __forceinline__ void eval_loaded(const Rec& cd, uint32_t q, double x1, double y1, double c1,
@@ -118,16 +90,6 @@ __device__ __forceinline__ void scan_range_staged(const Rec* stage, int32_t delt
                                                   uint32_t self_slot, Best& b) {
 #pragma unroll 2
     for (uint32_t q = qs; q < qe; ++q) eval_loaded<SELF>(stage[(int32_t)q + delta], q, x1, y1, c1, self_slot, b);
-}
-
-// Stop rule of qxmatch.hpp:336-340 on the small-angle forms. 0: stop for certain, 1: continue for
-// certain, 2: inside the slack. q1 is only known to lie in [q1_lo, q1_hi).
-__device__ __forceinline__ int stop_decision(double q1_lo, double q1_hi, double tr, const GridView& g) {
-    const double lo = tr - g.stop_delta, hi = tr + g.stop_delta;
-    if (lo > 0.0 && q1_hi*(1.0 + g.eps_hi) <= lo*lo*(1.0 - lo*lo*(1.0/12.0) - 1e-12)) return 0;
-    if (hi <= 0.0) return q1_lo > 0.0 ? 1 : 2;
-    if (q1_lo*(1.0 - g.eps_lo) > hi*hi) return 1;
-    return 2;
 }
 
 // merge the (smallest, second smallest, slot) triple of another candidate set into b
