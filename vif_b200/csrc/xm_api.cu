@@ -493,7 +493,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
                                                (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
                                                err, &launches))) return rc;
-        } else if (fast && self_mode != 2 && topk_filter_applicable(nth_eff)) {
+        } else if (!P.exact_only && fast_path_applicable(g) && topk_filter_applicable(nth_eff)) {
             // nth = 2..8: top-K filter kernel, exact kernel on the rows it flags (cells are in row order)
             XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
             if ((rc = launch_ring_topk_filter(g, *srcF, *v2, self, nth_eff, n1o, id, d, refine.as<uint32_t>(),

@@ -52,15 +52,15 @@ struct TopK {
 
 template <int K, bool SELF>
 __device__ __forceinline__ void scan_cell(const Rec* __restrict__ rec, uint32_t qs, uint32_t qe, double x1,
-                                          double y1, double c1, uint32_t self_slot, int twice, TopK<K>& L) {
+                                          double y1, double c1, uint32_t self_row, int twice, TopK<K>& L) {
     uint32_t q = qs;
     for (; q + 2 <= qe; q += 2) {
         const Rec r0 = load_rec(rec + q), r1 = load_rec(rec + q + 1);
         const double dx0 = r0.x - x1, dy0 = r0.y - y1, dx1 = r1.x - x1, dy1 = r1.y - y1;
         int32_t h0 = __double2hiint(fma(dx0*dx0*r0.c, c1, dy0*dy0));
         int32_t h1 = __double2hiint(fma(dx1*dx1*r1.c, c1, dy1*dy1));
-        if (SELF && q == self_slot) h0 = kInfHi;
-        if (SELF && q + 1 == self_slot) h1 = kInfHi;
+        if (SELF && r0.idx == self_row) h0 = kInfHi;      // never pair a source with itself (by original row)
+        if (SELF && r1.idx == self_row) h1 = kInfHi;
         if (h0 < L.h[K]) { L.insert(h0, q); if (twice) L.insert(h0, q); }
         if (h1 < L.h[K]) { L.insert(h1, q + 1); if (twice) L.insert(h1, q + 1); }
     }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void scan_cell(const Rec* __restrict__ rec, uint32_t 
         const Rec r0 = load_rec(rec + q);
         const double dx0 = r0.x - x1, dy0 = r0.y - y1;
         int32_t h0 = __double2hiint(fma(dx0*dx0*r0.c, c1, dy0*dy0));
-        if (SELF && q == self_slot) h0 = kInfHi;
+        if (SELF && r0.idx == self_row) h0 = kInfHi;
         if (h0 < L.h[K]) { L.insert(h0, q); if (twice) L.insert(h0, q); }
     }
 }
@@ -76,6 +76,7 @@ __device__ __forceinline__ void scan_cell(const Rec* __restrict__ rec, uint32_t 
 template <int K>
 struct TopkSmem {
     double   x[kThreads], y[kThreads], c[kThreads];
+    uint32_t row[kThreads];                  // original row of each source (self exclusion)
     uint2    range[kMaxItems];
     int32_t  thr[kMaxItems];                 // owner's (K+1)-th high word when the pair was queued
     int32_t  rh[kMaxItems][K + 1];           // partial lists of the queued pairs
@@ -116,7 +117,7 @@ ring_topk_filter_kernel(GridView g, CatView src, CatView cand, uint64_t plane_st
         // ---- ring 0: own cell --------------------------------------------------------------------
         {
             const uint32_t qs = cand.cstart[me.key], qe = cand.cstart[me.key + 1];
-            scan_cell<K, SELF>(cand.rec, qs, qe, x1, y1, c1, p, 0, L);
+            scan_cell<K, SELF>(cand.rec, qs, qe, x1, y1, c1, me.idx + g.self_off, 0, L);
             evals += qe - qs;
         }
         const double ex_lo = g.ox + (double)x0*g.wx, ey_lo = g.oy + (double)y0*g.wy;
@@ -162,6 +163,7 @@ ring_topk_filter_kernel(GridView g, CatView src, CatView cand, uint64_t plane_st
 
     // ---- queue the surviving non-empty (source, cell) pairs -------------------------------------------
     sm.x[threadIdx.x] = me.x; sm.y[threadIdx.x] = me.y; sm.c[threadIdx.x] = me.c;
+    sm.row[threadIdx.x] = me.idx + g.self_off;
     uint2 rng[kQueue];
     uint32_t tw = 0;                         // bit k: queued pair k counts twice
     uint32_t cnt = 0;
@@ -180,7 +182,7 @@ ring_topk_filter_kernel(GridView g, CatView src, CatView cand, uint64_t plane_st
                 tw |= (uint32_t)twice << cnt;
                 ++cnt;
             } else {
-                scan_cell<K, SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, p, twice, L);
+                scan_cell<K, SELF>(cand.rec, r.x, r.y, me.x, me.y, me.c, me.idx + g.self_off, twice, L);
                 evals += r.y - r.x;
             }
         }
@@ -214,7 +216,7 @@ ring_topk_filter_kernel(GridView g, CatView src, CatView cand, uint64_t plane_st
         const uint2 r = sm.range[it];
         TopK<K> A;
         A.init(sm.thr[it]);
-        scan_cell<K, SELF>(cand.rec, r.x, r.y, sm.x[owner], sm.y[owner], sm.c[owner], p0 + owner, 0, A);
+        scan_cell<K, SELF>(cand.rec, r.x, r.y, sm.x[owner], sm.y[owner], sm.c[owner], sm.row[owner], 0, A);
         evals += r.y - r.x;
 #pragma unroll
         for (int k = 0; k <= K; ++k) { sm.rh[it][k] = A.h[k]; sm.rs[it][k] = A.s[k]; }
