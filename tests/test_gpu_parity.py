@@ -283,3 +283,48 @@ def test_clean_best_device_matches_host():
     assert hp.id1.size + hp.lost.size == ra1.size and 0 < hp.lost.size < ra1.size
     # definition check
     assert np.all(host.rid[hp.id2] == hp.id1)
+
+
+def _random_case(rng):
+    """One random small problem: sizes, field, nth, flags."""
+    n1 = int(rng.integers(1, 4000)); n2 = int(rng.integers(1, 4000))
+    kind = rng.choice(["box", "tall", "wide", "tiny", "wrap", "dup"])
+    if kind == "box":
+        r0, rs, d0, ds = rng.uniform(0, 300), rng.uniform(0.05, 5), rng.uniform(-60, 55), rng.uniform(0.05, 5)
+    elif kind == "tall":
+        r0, rs, d0, ds = rng.uniform(0, 300), rng.uniform(0.1, 2), rng.uniform(-80, 20), rng.uniform(10, 50)
+    elif kind == "wide":
+        r0, rs, d0, ds = rng.uniform(0, 100), rng.uniform(20, 150), rng.uniform(-30, 20), rng.uniform(0.5, 5)
+    elif kind == "tiny":
+        r0, rs, d0, ds = rng.uniform(0, 359), 1e-3, rng.uniform(-80, 80), 1e-3
+    else:
+        r0, rs, d0, ds = rng.uniform(0, 300), rng.uniform(0.5, 3), rng.uniform(-40, 40), rng.uniform(0.5, 3)
+    ra1 = r0 + rs*rng.random(n1); dec1 = d0 + ds*rng.random(n1)
+    ra2 = r0 + rs*rng.random(n2); dec2 = d0 + ds*rng.random(n2)
+    if kind == "dup" and n2 > 4:
+        h = n2//2; ra2[h:2*h] = ra2[:h]; dec2[h:2*h] = dec2[:h]
+        m = min(n1, h); ra1[:m] = ra2[:m]; dec1[:m] = dec2[:m]          # zero distances too
+    kw = dict(nth=int(rng.choice([1, 1, 1, 2, 3, 5, 8, 9])))
+    if rng.random() < 0.25: kw["no_mirror"] = True
+    if rng.random() < 0.2: kw["brute_force"] = True
+    if rng.random() < 0.15 and kind != "wrap": kw["linear"] = True
+    self_match = rng.random() < 0.2
+    return kind, ra1, dec1, ra2, dec2, kw, self_match
+
+
+def test_random_differential(oracle):
+    """80 random small problems (sizes, fields, nth 1..9, self / no_mirror / brute_force / linear,
+    duplicated points) through every kernel family, each compared with the oracle."""
+    rng = np.random.default_rng(20261020)
+    seen = set()
+    for case in range(80):
+        kind, ra1, dec1, ra2, dec2, kw, self_match = _random_case(rng)
+        if self_match:
+            exp = oracle.oracle_qxmatch(ra1, dec1, ra1, dec1, thread=4, self=True, **kw)
+            got = qxmatch(ra1, dec1, **kw)
+        else:
+            exp = oracle.oracle_qxmatch(ra1, dec1, ra2, dec2, thread=4, **kw)
+            got = qxmatch(ra1, dec1, ra2, dec2, **kw)
+        assert_same_result(got, exp, RTOL, f"case {case} {kind} n=({ra1.size},{ra2.size}) self={self_match} {kw}")
+        seen.add((kind, kw["nth"] > 1, bool(kw.get("brute_force")), self_match))
+    assert len(seen) > 25          # the draw did spread over the families
