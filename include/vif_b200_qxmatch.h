@@ -120,6 +120,12 @@ int32_t xm_init(int32_t device, char* errbuf, uint64_t errcap);
 /* Releases all contexts and device memory owned by the library. */
 void xm_shutdown(void);
 
+/* Scratch memory is drawn from the device's stream-ordered pool and stays cached there between
+ * calls (a 1e9-row call re-maps ~80 GB otherwise, four times the cost of its index build). This
+ * hands the cached memory back to the driver; the environment variable XM_POOL_KEEP_GB caps what
+ * the pool keeps instead. device = -1 -> current. Returns XM_OK or XM_ERR_CUDA. */
+int32_t xm_release_memory(int32_t device);
+
 /*
  * qxmatch on HOST buffers (the reference-facing call; replaces qxmatch.hpp:133-616).
  *   ra1,dec1: n1 doubles; ra2,dec2: n2 doubles.

@@ -18,11 +18,11 @@ def gen(seed, n):   # chunked to bound temporaries
 ra1, dec1 = gen(1, n1); ra2, dec2 = gen(2, n2)
 torch.cuda.synchronize()
 print("generated", n1, n2, "free GB", torch.cuda.mem_get_info()[0]/1e9, flush=True)
-for it in range(2):
+for it in range(int(os.environ.get("ITERS", "2"))):
     t = time.time(); r = qxmatch(ra1, dec1, ra2, dec2); torch.cuda.synchronize(); w = time.time() - t
     st = r.stats
     print(f"C5 {n1:.0e}x{n2:.0e}: wall {w:.3f}s total {st['ms_total']:.1f} ms (index {st['ms_index']:.1f} fwd {st['ms_forward']:.1f} rev {st['ms_reverse']:.1f}) "
-          f"-> {n1/(st['ms_total']*1e-3):.3e} src/s; evals/src fwd {st['evals_fwd']/n1:.1f} rev {st['evals_rev']/n2:.1f}; grid {st['grid']['nra']}x{st['grid']['ndec']} cell {st['grid']['cell_size']:.1f}\"", flush=True)
+          f"-> {n1/(st['ms_total']*1e-3):.3e} src/s; evals/src fwd {st['evals_fwd']/n1:.1f} rev {st['evals_rev']/n2:.1f}; grid {st['grid']['nra']}x{st['grid']['ndec']} cell {st["grid"]["cell_size"]:.1f}\" refined {st["rows_refined_fwd"]}/{st["rows_refined_rev"]}", flush=True)
 sel = torch.arange(0, n1, n1//48, device="cuda")[:48]
 h2, k2 = ra2.cpu().numpy(), dec2.cpu().numpy()
 exp = O.oracle_qxmatch(ra1[sel].cpu().numpy(), dec1[sel].cpu().numpy(), h2, k2, brute_force=True, no_mirror=True, thread=os.cpu_count())

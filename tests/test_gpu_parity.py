@@ -184,6 +184,38 @@ def test_exact_grid_equals_brute_force(oracle, name, c1, c2, kw):
     assert got.stats["evals_fwd"] < 0.5*c1[0].size*c2[0].size or c2[0].size < 100      # it did not scan all pairs
 
 
+def _sphere_nn_cases():
+    band = lambda seed, n: (360.0*G.uniform(seed, 0, n), -1.0 + 2.0*G.uniform(seed, 1, n))
+    yield "compact_box", G.c1(61, 20_000), G.c1(62, 20_000), dict()
+    yield "band_all_ra", band(63, 20_000), band(64, 22_000), dict()
+    b2 = band(65, 20_000); b2[0][10_000:] = b2[0][:10_000]; b2[1][10_000:] = b2[1][:10_000]
+    yield "band_duplicates", band(66, 9_000), b2, dict()
+    yield "band_no_mirror", band(67, 9_000), band(68, 20_000), dict(no_mirror=True)
+    yield "uneven_density", G.c1(69, 3_000), G.c1(70, 40_000), dict()
+
+
+@pytest.mark.parametrize("name,c1,c2,kw", list(_sphere_nn_cases()), ids=[c[0] for c in _sphere_nn_cases()])
+def test_exact_grid_nearest_filter(oracle, name, c1, c2, kw):
+    """nth = 1 on small cells goes through the spherical filter kernel + list-mode exact kernel."""
+    exp = oracle.oracle_qxmatch(c1[0], c1[1], c2[0], c2[1], brute_force=True, thread=os.cpu_count() or 8, **kw)
+    got = qxmatch(c1[0], c1[1], c2[0], c2[1], brute_force=True, exact_grid=True, **kw)
+    assert_same_result(got, exp, RTOL, name)
+    refined = got.stats["rows_refined_fwd"]                        # the filter ran and decided most rows
+    if name == "band_duplicates":                                  # ... except where every candidate has an exact twin
+        assert refined == c1[0].size
+    else:
+        assert 0 < refined < 0.5*c1[0].size
+
+
+def test_exact_grid_nearest_filter_self(oracle):
+    ra, dec = G.c1(71, 25_000)
+    ra[20_000:] = ra[:5_000]; dec[20_000:] = dec[:5_000]            # exact duplicates at distance 0
+    exp = oracle.oracle_qxmatch(ra, dec, ra, dec, brute_force=True, self=True, thread=os.cpu_count() or 8)
+    got = qxmatch(ra, dec, brute_force=True, exact_grid=True)
+    assert_same_result(got, exp, RTOL, "sphere-self-nn")
+    assert 0 < got.stats["rows_refined_fwd"] < 0.6*ra.size
+
+
 def test_exact_grid_self(oracle):
     ra, dec = G.fullsky(55, 15_000)
     exp = oracle.oracle_qxmatch(ra, dec, ra, dec, brute_force=True, self=True, nth=3, thread=os.cpu_count() or 8)

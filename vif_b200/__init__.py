@@ -12,6 +12,6 @@ There is no CPU implementation in this package: without the CUDA library and a G
 entry point raises.
 """
 from .qxmatch import (QxmatchParams, QxmatchRes, QxmatchError, IdPair, qxmatch, xmatch_clean_best,  # noqa: F401
-                      last_stats, NPOS)
+                      last_stats, release_memory, NPOS)
 
 __version__ = "0.1"

@@ -42,7 +42,7 @@ class XmStats(C.Structure):
 
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
-SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_qxmatch_f64", "xm_qxmatch_dev",
+SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
            "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
@@ -65,6 +65,8 @@ def load():
     lib.xm_init.argtypes = [i32, C.c_char_p, u64]
     lib.xm_shutdown.restype = None
     lib.xm_shutdown.argtypes = []
+    lib.xm_release_memory.restype = C.c_int32
+    lib.xm_release_memory.argtypes = [C.c_int32]
     sig = [vp, vp, u64, vp, vp, u64, C.POINTER(XmParams), vp, vp, vp, vp]
     lib.xm_qxmatch_f64.restype = i32
     lib.xm_qxmatch_f64.argtypes = sig + [C.c_char_p, u64]

@@ -78,11 +78,13 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     XM_CUDA_TRY(cudaMalloc(&c->d_ctr, sizeof(SearchCounters)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_ctr, sizeof(SearchCounters)));
     for (auto& e : c->ev) XM_CUDA_TRY(cudaEventCreate(&e));
-    // keep up to 8 GB of freed scratch in the stream-ordered pool: repeated calls on the benchmark
-    // sizes never hit cudaMalloc, while a 1e9-row call hands its ~80 GB back at the next sync
+    // freed scratch stays in the stream-ordered pool: repeated calls never go back to the driver for
+    // memory (measured on 1e9 x 1e8: index build 60 ms with the pool warm, 230 ms when the pool had
+    // to re-map its ~80 GB every call). xm_release_memory() / XM_POOL_KEEP_GB bound the footprint.
     cudaMemPool_t pool;
     XM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = 8ull << 30;
+    uint64_t keep = ~0ull;
+    if (const char* e = getenv("XM_POOL_KEEP_GB")) keep = (uint64_t)strtoull(e, nullptr, 10) << 30;
     XM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     c->sin_model = calibrate_sin_model();
     XM_CUDA_TRY(cudaSetDevice(prev));
@@ -217,12 +219,21 @@ int32_t run_sphere(Context* ctx, cudaStream_t s, const double* ra1, const double
     XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[2], 0));
     XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[1], 0));
     XM_CUDA_TRY(cudaEventRecord(ev[5], s));
-    if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), s1.view, *v2, self, nth, n1, id, d, false,
-                                   ctx->d_ctr, s, err, launches))) return rc;
+    // nth = 1: undecided-row lists of the filter kernel and its sector-sized result records (the records
+    // are optional: a catalog too large to afford 32 bytes per row scatters 8-byte stores instead)
+    Scratch rl1, rl2, rr1, rr2;
+    XM_CUDA_TRY(rl1.alloc((size_t)n1*4, s));
+    if (nth == 1 && rr1.alloc(filter_result_bytes(n1), s) != cudaSuccess) { cudaGetLastError(); rr1.p = nullptr; }
+    if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), s1.view, *v2, self, nth, n1, id, d, rl1.as<uint32_t>(),
+                                   &ctx->d_ctr->refine_fwd, rr1.p, false, ctx->d_ctr, s, err, launches))) return rc;
     XM_CUDA_TRY(cudaEventRecord(ev[6], s));
     XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
-    if (mirror && (rc = launch_sphere_search(g, wrap, cmin.as<double>(), *v2, s1.view, self, 1u, n2, rid, rd, true,
-                                             ctx->d_ctr, s2, err, launches))) return rc;
+    if (mirror) {
+        XM_CUDA_TRY(rl2.alloc((size_t)n2*4, s2));
+        if (rr2.alloc(filter_result_bytes(n2), s2) != cudaSuccess) { cudaGetLastError(); rr2.p = nullptr; }
+        if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), *v2, s1.view, self, 1u, n2, rid, rd, rl2.as<uint32_t>(),
+                                       &ctx->d_ctr->refine_rev, rr2.p, true, ctx->d_ctr, s2, err, launches))) return rc;
+    }
     XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
     XM_CUDA_TRY(cudaEventRecord(sev[3], s2));
     XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[3], 0));
@@ -643,6 +654,18 @@ void xm_shutdown(void) {
         cudaStreamDestroy(c->stream);
     }
     g_ctx.clear();
+}
+
+int32_t xm_release_memory(int32_t device) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return XM_ERR_CUDA; }
+    if (device < 0) device = prev;
+    cudaMemPool_t pool;
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
+              cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && cudaMemPoolTrimTo(pool, 0) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    cudaSetDevice(prev);
+    return ok ? XM_OK : XM_ERR_CUDA;
 }
 
 int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,

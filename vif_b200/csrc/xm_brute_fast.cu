@@ -305,7 +305,7 @@ int32_t launch_unit_vectors(const double* x, const double* y, const double* c, u
     return XM_OK;
 }
 
-bool brute_fast_applicable(bool linear, uint32_t nth) { return !linear && nth >= 1 && nth <= 4; }
+bool brute_fast_applicable(bool linear, uint32_t nth) { return !linear && nth >= 1 && nth <= 8; }
 
 int32_t launch_brute_fast(int sin_model, const void* u1, uint32_t n1, const void* u2, uint32_t n2,
                           const double* x1, const double* y1, const double* c1, const double* x2,
@@ -322,7 +322,15 @@ int32_t launch_brute_fast(int sin_model, const void* u1, uint32_t n1, const void
                                         id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
     case 3: return run_brute_fast<3, 2>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
                                         id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
-    default: return run_brute_fast<4, 2>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
+    case 4: return run_brute_fast<4, 2>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
+                                        id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
+    case 5: return run_brute_fast<5, 1>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
+                                        id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
+    case 6: return run_brute_fast<6, 1>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
+                                        id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
+    case 7: return run_brute_fast<7, 1>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
+                                        id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
+    default: return run_brute_fast<8, 1>(sin_model, a, n1, b, n2, x1, y1, c1, x2, y2, c2, self, plane_stride,
                                          id_out, d_out, refine_list, refine_thr, refine_count, ctr, s, err, launches);
     }
 }

@@ -119,6 +119,8 @@ int32_t launch_row_tables(const GridView& g, double* cmin_row, double* ccen_row,
 // decide rigorously are appended to refine_list (count in *refine_count) for the exact kernel
 bool    fast_path_applicable(const GridView& g);
 size_t  filter_result_bytes(uint64_t n);     // scratch for the filter's sector-sized result records
+int32_t launch_unpack_results(const void* res, uint32_t n, uint64_t* id_out, double* d_out, cudaStream_t s,
+                              Error& err, uint64_t* launches);
 size_t  filter_plan_bytes(uint64_t n);       // scratch for the per-tile staging plans
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
@@ -136,7 +138,7 @@ int32_t launch_ring_topk_filter(const GridView& g, const CatView& src, const Cat
                                 uint32_t nth_eff, uint64_t plane_stride, uint64_t* id_out, double* d_out,
                                 uint32_t* refine_list, unsigned long long* refine_count, SearchCounters* ctr,
                                 cudaStream_t s, Error& err, uint64_t* launches);
-// xm_brute_fast.cu: dot-product filter + exact refine for brute_force (spherical, nth <= 4)
+// xm_brute_fast.cu: dot-product filter + exact refine for brute_force (spherical, nth <= 8)
 size_t  brute_uvec_bytes(uint64_t n);
 bool    brute_fast_applicable(bool linear, uint32_t nth);
 int32_t launch_unit_vectors(const double* x, const double* y, const double* c, uint32_t n, void* out,
@@ -153,8 +155,9 @@ bool    sphere_applicable(bool linear, uint32_t nth);
 int32_t launch_sphere_rows(const GridView& g, double* cmin_row, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row, const CatView& src,
                              const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
-                             uint64_t* id_out, double* d_out, bool reverse, SearchCounters* ctr,
-                             cudaStream_t s, Error& err, uint64_t* launches);
+                             uint64_t* id_out, double* d_out, uint32_t* refine_list,
+                             unsigned long long* refine_count, void* result_records, bool reverse,
+                             SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
                              uint64_t* launches);

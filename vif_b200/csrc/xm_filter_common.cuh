@@ -24,6 +24,14 @@ __device__ __forceinline__ Rec load_rec(const Rec* p) {
     return r;
 }
 
+// result of one source, padded to a DRAM sector (a scattered 8-byte store costs a read-modify-write
+// of the sector); unpack_results_kernel splits the records into id[] / d[] with coalesced accesses
+struct __align__(32) ResRec { uint64_t id; double d; uint64_t pad0, pad1; };
+
+__device__ __forceinline__ void store_res(ResRec* p, uint64_t id, double d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%3};" :: "l"(p), "l"(id), "l"(__double_as_longlong(d)), "l"(0ll) : "memory");
+}
+
 // Running state of one source. Q >= 0, so the high 32 bits of its IEEE pattern are a monotone
 // 21-bit-mantissa image of it: the loop tracks the smallest and second smallest HIGH WORDS with
 // native 32-bit integer min/max (FP64 min/max are multi-instruction selects on sm_100) and the slot

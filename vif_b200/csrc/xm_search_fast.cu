@@ -32,13 +32,6 @@ using namespace filt;
 
 constexpr int kThreads = 256;
 
-// result of one source, padded to a DRAM sector; unpack_results_kernel splits it into id[] / d[]
-struct __align__(32) ResRec { uint64_t id; double d; uint64_t pad0, pad1; };
-
-__device__ __forceinline__ void store_res(ResRec* p, uint64_t id, double d) {
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%3};" :: "l"(p), "l"(id), "l"(__double_as_longlong(d)), "l"(0ll) : "memory");
-}
-
 struct Best {
     int32_t h1, h2;
     uint32_t slot;
@@ -435,6 +428,15 @@ unpack_results_kernel(const ResRec* __restrict__ res, uint32_t n, uint64_t* __re
 }  // namespace
 
 size_t filter_result_bytes(uint64_t n) { return (size_t)n*sizeof(ResRec); }
+
+int32_t launch_unpack_results(const void* res, uint32_t n, uint64_t* id_out, double* d_out, cudaStream_t s,
+                              Error& err, uint64_t* launches) {
+    if (n == 0) return XM_OK;
+    unpack_results_kernel<<<(n + 255)/256, 256, 0, s>>>((const ResRec*)res, n, id_out, d_out);
+    *launches += 1;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
 
 // The filter's bounds assume small cells well away from the poles; everything else is the exact
 // kernel's job.

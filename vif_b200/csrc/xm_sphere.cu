@@ -19,6 +19,7 @@
 // reference-order proxy (xm_math_exact.cuh) and inserted by (proxy, row) lexicographic order.
 #include "xm_common.cuh"
 #include "xm_math_exact.cuh"
+#include "xm_filter_common.cuh"
 
 namespace xm {
 
@@ -69,11 +70,16 @@ template <int K>
 __global__ void __launch_bounds__(kThreads)
 sphere_search_kernel(SphereGrid sg, CatView src, CatView cand, int self_mode, uint32_t nth_eff,
                      uint64_t plane_stride, uint64_t* __restrict__ id_out, double* __restrict__ d_out,
+                     const uint32_t* __restrict__ rows, const unsigned long long* __restrict__ nrows_dev,
                      int reverse, SearchCounters* ctr) {
     const GridView& g = sg.g;
-    const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    // rows == nullptr: thread t handles sorted slot t; otherwise a grid-stride walk over the row list
+    // whose length lives on the device (rows the filter kernel could not decide)
+    const uint32_t nrows = rows ? (uint32_t)min((unsigned long long)src.n, *nrows_dev) : src.n;
+    const uint32_t stride = gridDim.x*blockDim.x;
     unsigned long long evals = 0;
-    if (p < src.n) {
+    for (uint32_t t = blockIdx.x*blockDim.x + threadIdx.x; t < nrows; t += stride) {
+        const uint32_t p = rows ? rows[t] : t;
         const Rec me = src.rec[p];
         const double x1 = me.x, y1 = me.y, c1 = me.c < 0.0 ? 0.0 : me.c;
         const int ncol = (int)g.nra, nrow = (int)g.ndec;
@@ -175,6 +181,111 @@ sphere_search_kernel(SphereGrid sg, CatView src, CatView cand, int self_mode, ui
     if ((threadIdx.x & 31) == 0 && evals) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, evals);
 }
 
+// ---- nearest-neighbour filter (nth = 1) ------------------------------------------------------------------
+// Same contract as ring_nn_filter_kernel of the cell-binned path: rank the candidates of the 3x3 cell
+// block with the cheap metric Q = dy^2 + dx^2 cos cos (dx wrapped into [-pi, pi]), tracked by its high
+// word; accept the row only if (1) everything outside the block is provably farther than the winner and
+// (2) the winner beats the runner-up by more than the metric's uncertainty (4p in [Q(1 - M/12), Q],
+// M <= (2 max(w))^2 inside the block); then evaluate the reference-order proxy of the winning pair once.
+// Any other row is appended to the list the exact kernel above walks afterwards.
+// The body is kept small on purpose (one rolled loop over the nine cells, polynomial bounds, the
+// small-angle sine only): the first version unrolled everything, grew to 4700 SASS instructions and
+// spent 58 % of its issue slots waiting for instruction fetches.
+using filt::kInfHi; using filt::hi_floor; using filt::hi_ceil; using filt::ResRec; using filt::store_res;
+
+// cell order: own, N, S, E, W, NE, NW, SE, SW (sides before corners, so that the best shrinks early);
+// two bits per entry hold offset + 1
+constexpr uint32_t pack9(int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7, int a8) {
+    return (uint32_t)(a0 + 1) | (uint32_t)(a1 + 1) << 2 | (uint32_t)(a2 + 1) << 4 | (uint32_t)(a3 + 1) << 6 |
+           (uint32_t)(a4 + 1) << 8 | (uint32_t)(a5 + 1) << 10 | (uint32_t)(a6 + 1) << 12 |
+           (uint32_t)(a7 + 1) << 14 | (uint32_t)(a8 + 1) << 16;
+}
+constexpr uint32_t kNbX = pack9(0, 0, 0, 1, -1, 1, -1, 1, -1);
+constexpr uint32_t kNbY = pack9(0, 1, -1, 0, 0, 1, 1, -1, -1);
+
+template <bool SELF, bool WRAP>
+__global__ void __launch_bounds__(kThreads)
+sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo, ResRec* __restrict__ res,
+                        uint64_t* __restrict__ id_out, double* __restrict__ d_out,
+                        uint32_t* __restrict__ refine_list, unsigned long long* refine_count, int reverse,
+                        SearchCounters* ctr) {
+    const GridView& g = sg.g;
+    const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    uint32_t evals = 0;
+    if (p < src.n) {
+        const Rec me = filt::load_rec(src.rec + p);
+        const double x1 = me.x, y1 = me.y, c1 = me.c;
+        const int ncol = (int)g.nra, nrow = (int)g.ndec;
+        const int x0 = (int)(me.key/g.ndec), y0 = (int)(me.key - (uint32_t)x0*g.ndec);
+        const double wx = g.wx, wy = g.wy;
+        bool flag = !(c1 >= 0.0) || y0 < 1 || y0 + 1 >= nrow || (!WRAP && (x0 < 1 || x0 + 1 >= ncol));
+        int32_t h1 = kInfHi, h2 = kInfHi;
+        uint32_t slot = kNone;
+        if (!flag) {
+            // key offsets of the east / west columns (modulo the circle in wrap mode)
+            int32_t de = (int32_t)g.ndec, dw = -(int32_t)g.ndec;
+            if (WRAP) { if (x0 + 1 >= ncol) de -= (int32_t)(g.ndec*g.nra); if (x0 < 1) dw += (int32_t)(g.ndec*g.nra); }
+            const double cx_lo = g.ox + (double)x0*wx, cy_lo = g.oy + (double)y0*wy;
+            double ge = cx_lo + wx - x1 - g.fzx, gw = x1 - cx_lo - g.fzx;
+            double gn = cy_lo + wy - y1 - g.fzy, gs = y1 - cy_lo - g.fzy;
+            ge = ge > 0 ? ge : 0; gw = gw > 0 ? gw : 0; gn = gn > 0 ? gn : 0; gs = gs > 0 ? gs : 0;
+            const double shrink = 1.0 - eps_lo - 1e-9;
+            const double cm0 = sg.cmin_row[y0]*c1, cmn = sg.cmin_row[y0 + 1]*c1, cms = sg.cmin_row[y0 - 1]*c1;
+#pragma unroll 1
+            for (int e = 0; e < 9; ++e) {
+                const int bx = (int)((kNbX >> (2*e)) & 3u) - 1, by = (int)((kNbY >> (2*e)) & 3u) - 1;
+                const double gx = bx > 0 ? ge : (bx < 0 ? gw : 0.0), gy = by > 0 ? gn : (by < 0 ? gs : 0.0);
+                const double cm = by > 0 ? cmn : (by < 0 ? cms : cm0);
+                // lower bound (in Q) of the cell's candidates against the current best
+                const double lb = fma(gx*gx, cm, gy*gy)*shrink;
+                if (e > 0 && !(lb < hi_ceil(h1)*(1.0 + 1e-9))) continue;
+                const uint32_t k = me.key + (uint32_t)(bx > 0 ? de : (bx < 0 ? dw : 0)) + (uint32_t)by;
+                const uint32_t qs = cand.cstart[k], qe = cand.cstart[k + 1];
+                for (uint32_t q = qs; q < qe; ++q) {
+                    const Rec cd = filt::load_rec(cand.rec + q);
+                    double dx = cd.x - x1;
+                    const double dy = cd.y - y1;
+                    if (WRAP) dx = dx > 3.141592653589793 ? dx - 6.283185307179586 : (dx < -3.141592653589793 ? dx + 6.283185307179586 : dx);
+                    int32_t h = __double2hiint(fma(dx*dx*cd.c, c1, dy*dy));
+                    if (SELF && cd.idx == me.idx) h = kInfHi;
+                    const bool better = h < h1;
+                    h2 = min(h2, max(h1, h));
+                    h1 = min(h1, h);
+                    slot = better ? q : slot;
+                }
+                evals += qe - qs;
+            }
+            // (1) completeness: proxy bounds of everything outside the 3x3 block, with
+            // sin^2 h >= h^2 (1 - h^2/3) for every h; (2) winner vs runner-up
+            const double oy = wy - 2.0*g.fzy, ox = wx - 2.0*g.fzx;      // binning slack of the far cells
+            const double hy = 0.5*(fmin(gn, gs) + oy), hx = 0.5*fmin(fmin(ge, gw) + ox, 3.141592653589793);
+            const double cmin3 = fmin(fmin(cm0, cmn), cms);
+            const double out_p = fmin(hy*hy*(1.0 - hy*hy*(1.0/3.0)), hx*hx*(1.0 - hx*hx*(1.0/3.0))*cmin3)*(1.0 - 1e-9);
+            const double q1 = hi_ceil(h1);
+            if (!(0.25*q1*(1.0 + 1e-9) <= out_p)) flag = true;
+            if (h2 < kInfHi && !(q1*(1.0 + 1e-12) < hi_floor(h2)*shrink)) flag = true;
+            if (slot == kNone || h1 < 0) flag = true;
+        }
+        Rec w;
+        if (!flag) {
+            w = filt::load_rec(cand.rec + slot);
+            // the small-angle sine covers |dx|/2 < 0.126; pairs across the RA seam go to the exact kernel
+            if (!(fabs(w.x - x1) < 0.25 && fabs(w.y - y1) < 0.25)) flag = true;
+        }
+        if (flag) {
+            const unsigned long long pos = atomicAdd(refine_count, 1ull);
+            refine_list[pos] = p;
+        } else {
+            const double dist = proxy_to_true_small(proxy_sph_small(x1, y1, c1, w.x, w.y, w.c, g.sin_model));
+            if (res) store_res(res + me.idx, (uint64_t)w.idx, dist);
+            else { id_out[me.idx] = (uint64_t)w.idx; d_out[me.idx] = dist; }
+        }
+    }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
+    if ((threadIdx.x & 31) == 0 && evals) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, (unsigned long long)evals);
+}
+
 __global__ void sphere_rows_kernel(GridView g, double* __restrict__ cmin) {
     const uint32_t r = blockIdx.x*blockDim.x + threadIdx.x;
     if (r >= g.ndec) return;
@@ -237,14 +348,36 @@ bool sphere_applicable(bool linear, uint32_t nth) { return !linear && nth >= 1 &
 
 int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row, const CatView& src,
                              const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
-                             uint64_t* id_out, double* d_out, bool reverse, SearchCounters* ctr,
-                             cudaStream_t s, Error& err, uint64_t* launches) {
+                             uint64_t* id_out, double* d_out, uint32_t* refine_list,
+                             unsigned long long* refine_count, void* result_records, bool reverse,
+                             SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches) {
     if (src.n == 0 || nth_eff == 0) return XM_OK;
     SphereGrid sg;
     sg.g = g; sg.wrap = wrap; sg.cmin_row = cmin_row;
-    const dim3 grid((src.n + kThreads - 1)/kThreads);
+    const dim3 full((src.n + kThreads - 1)/kThreads);
+    // nth = 1 on small cells: filter kernel first, the exact kernel then walks the rows it flagged
+    const double wmax = g.wx > g.wy ? g.wx : g.wy;
+    const bool filter = nth_eff == 1 && refine_list && wmax <= 0.02 && g.nra >= 8 && g.ndec >= 3;
+    const uint32_t* rows = nullptr;
+    dim3 grid = full;
+    if (filter) {
+        const double eps_lo = (2.0*wmax)*(2.0*wmax)/12.0 + 1e-14;
+        ResRec* res = (ResRec*)result_records;
+        const int rv = reverse ? 1 : 0;
+#define XM_FILT(S, W) sphere_nn_filter_kernel<S, W><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, \
+        d_out, refine_list, refine_count, rv, ctr)
+        if (self) { if (wrap) XM_FILT(true, true); else XM_FILT(true, false); }
+        else { if (wrap) XM_FILT(false, true); else XM_FILT(false, false); }
+#undef XM_FILT
+        XM_CUDA_TRY(cudaGetLastError());
+        // rows flagged for the exact kernel carry garbage in their records; it overwrites them afterwards
+        if (res) { int32_t rc = launch_unpack_results(res, src.n, id_out, d_out, s, err, launches); if (rc) return rc; }
+        *launches += 1;
+        rows = refine_list;
+        if (grid.x > 148*8) grid.x = 148*8;
+    }
 #define XM_CASE(KK) case KK: sphere_search_kernel<KK><<<grid, kThreads, 0, s>>>(sg, src, cand, self ? 1 : 0, \
-        nth_eff, plane_stride, id_out, d_out, reverse ? 1 : 0, ctr); break;
+        nth_eff, plane_stride, id_out, d_out, rows, refine_count, reverse ? 1 : 0, ctr); break;
     switch (nth_eff) { XM_CASE(1) XM_CASE(2) XM_CASE(3) XM_CASE(4) XM_CASE(5) XM_CASE(6) XM_CASE(7) default: XM_CASE(8) }
 #undef XM_CASE
     *launches += 1;

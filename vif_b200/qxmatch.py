@@ -102,6 +102,13 @@ def last_stats(device=-1):
     return st.as_dict()
 
 
+def release_memory(device=-1):
+    """Hands the scratch memory cached between calls back to the driver (xm_release_memory)."""
+    rc = _lib.load().xm_release_memory(int(device))
+    if rc != _lib.XM_OK:
+        raise QxmatchError(rc, "xm_release_memory failed")
+
+
 def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, out=None, **kw):
     """See module docstring. `params` may be a QxmatchParams; keywords override its fields.
     `out` (host path only): dict of preallocated numpy arrays id/d/rid/rd to receive the results,
