@@ -160,9 +160,10 @@ def run_reference_arm(args):
     v = SAMPLE_N / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(N_FULL, N_FULL), "nth": 1, "sample": desc},
+        "config": {"workload": workload_desc(N_FULL * (args.gpus if args.scaling == "weak" else 1), N_FULL), "nth": 1,
+                   "sample": desc},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -186,7 +187,8 @@ def run_gpu_arm(args):
     if world > 1:
         os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
-    n1 = args.n
+    # weak scaling (c2 default): every rank brings args.n rows of catalog 1, catalog 2 stays args.n rows
+    n1 = args.n * world if args.scaling == "weak" else args.n
     n2 = args.n2 if args.n2 else (args.n // 10 if args.config == "c5" else args.n)
     lo, hi = shard_bounds(n1, world, rank)
     if args.config == "c3":
@@ -221,8 +223,8 @@ def run_gpu_arm(args):
         elif world == 1:
             r = qxmatch(ra1, dec1, ra2, dec2, params=params)
             out = (r.id, r.d, r.rid, r.rd)
-        elif args.config == "c2":
-            # catalogs small enough to replicate: row blocks of BOTH catalogs per rank, no merge
+        elif args.config == "c2" and args.scaling == "strong":
+            # fixed 1e7 x 1e7: catalogs small enough to replicate, row blocks of BOTH per rank, no merge
             out = qxmatch_partitioned(ra1, dec1, ra2, dec2, lo, n1, params)
         else:
             out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
@@ -247,13 +249,17 @@ def run_gpu_arm(args):
         step(False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     for k in range(args.steps):
         out = step(True)
+        marks[k].record()
         if rank == 0:
             sampler.sample()                # a few microseconds; between two steps of the timed region
     e1.record()
     barrier()
+    per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    args.step_ms = {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)}
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     launches = torch.tensor([stats_acc["launches"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -305,7 +311,7 @@ def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev
             if rank == 0:
                 ra2.copy_(h["ra2"], non_blocking=True)
                 dec2.copy_(h["dec2"], non_blocking=True)
-            if args.config == "c2":
+            if args.config == "c2" and args.scaling == "strong":
                 from vif_b200.distributed import qxmatch_partitioned
                 i_, d_, rid_, rd_, _ = qxmatch_partitioned(a, b, ra2, dec2, lo, n1, params)
                 o["rid"][:rid_.numel()].copy_(rid_, non_blocking=True)      # every rank returns its block
@@ -356,19 +362,23 @@ def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_ac
         whole_bytes = 16 * n1 + 16 * n2 + 16 * n1 + 16 * n2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_desc(n1, n2, args.config), "n1": n1, "n2": n2, "nth": 1,
                        "l2": "no flush: the 320 MB of input coordinates plus the ~0.5 GB cell index exceed the 126 MB L2",
                        "parallelism": ("1 rank" if world == 1 else
                                        ("catalog 2 NCCL-broadcast, catalog-1 row shards NCCL-all-gathered; each of the %d ranks "
                                         "matches its row block of catalog 1 (forward) and of catalog 2 (reverse) against the "
-                                        "whole other catalog; no merge collective" % world) if args.config == "c2" else
-                                       ("catalog-1 rows sharded over %d ranks; catalog 2 NCCL-broadcast and indexed per rank; "
-                                        "reverse match merged with all-reduce(min)" % world))},
+                                        "whole other catalog; no merge collective" % world)
+                                       if args.config == "c2" and args.scaling == "strong" else
+                                       ("catalog-1 rows sharded over %d ranks (%d rows each); catalog 2 NCCL-broadcast and "
+                                        "indexed per rank; reverse match merged by one kernel over NVLink peer memory "
+                                        "(xm_rev_merge_p2p; NCCL all-reduce(min) when peer mappings are unavailable)"
+                                        % (world, hi - lo)))},
             "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "ms_per_step": dt.item() * 1e3, "steps": e2e_steps} if e2e_value is not None else None),
             "gpu_launches": int(launches.item()),
+            "step_ms_rank0": args.step_ms,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": ("sphere_search_kernel (forward + reverse launches)" if args.config == "c5" else
                                                    "ring_nn_filter_kernel (forward + reverse launches, run concurrently)"), "achieved": achieved,
@@ -409,11 +419,16 @@ def main():
     ap.add_argument("--rows2", dest="n2", type=int, default=None, help="rows of catalog 2 (default: n for c2, n/10 for c5)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2 = the headline metric's workload (default); c5 = 1e9 x 1e8 full sky (manual scaling runs)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="N>1: weak = every rank brings --rows rows of catalog 1 against the same catalog 2 (c2 default: "
+                         "the path shards by catalog-1 rows); strong = the total stays --rows (c3/c5 default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.n is None:
         args.n = {"c5": 1_000_000_000, "c3": 100_000_000}.get(args.config, N_FULL)
+    if args.scaling == "auto":
+        args.scaling = "weak" if args.config == "c2" else "strong"
     if args.config == "c3":
         args.no_e2e = True
     if args.impl == "reference":

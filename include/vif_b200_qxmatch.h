@@ -187,6 +187,22 @@ int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, u
                             int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
 /*
+ * The same merge as ONE kernel over NVLink peer memory (no NCCL collective on the data path).
+ *   exch[r], r < world: peer-mapped device pointer to rank r's exchange buffer of 2n+1 8-byte
+ *                       words: its n local rd (double), its n local rid (uint64, XM_NPOS =
+ *                       unmatched) as xm_qxmatch_dev returned them, and its first catalog-1 row;
+ *   out[r]:             peer-mapped pointer to rank r's result buffer: n rd, then n rid.
+ * The calling rank merges rows [n*rank/world, n*(rank+1)/world) -- smallest distance, smallest
+ * global row id among equal distances (qxmatch.hpp:510-513) -- and stores them into EVERY out[r].
+ * The caller brackets the call with barriers over the ranks: all exchange buffers filled before,
+ * all stores landed after (vif_b200/distributed.py uses torch symmetric memory for both).
+ * world <= XM_MAX_PEERS. Launches on `stream` and returns without synchronising.
+ */
+#define XM_MAX_PEERS 16
+int32_t xm_rev_merge_p2p(const void* const* exch, void* const* out, uint64_t n, int32_t rank, int32_t world,
+                         double unmatched, int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
+/*
  * Mutual-best filter on the device (replaces xmatch_clean_best, qxmatch.hpp:641-663, while id/rid
  * are still resident): row i of catalog 1 is kept when rid[id[i]] == i. id = rank-0 plane (n1), rid
  * (n2). Outputs (caller-allocated, n1 elements each): id1/id2 = the kept pairs in ascending i, lost =

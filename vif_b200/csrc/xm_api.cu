@@ -855,6 +855,28 @@ int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, u
     return merge_entry(2, rid, rd, nullptr, key_best, nullptr, n, 0, unmatched, device, stream, errbuf, errcap);
 }
 
+int32_t xm_rev_merge_p2p(const void* const* exch, void* const* out, uint64_t n, int32_t rank, int32_t world,
+                         double unmatched, int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = (!exch || !out || world < 1 || world > XM_MAX_PEERS || rank < 0 || rank >= world)
+                     ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    for (int r = 0; !rc && r < world; ++r)
+        if (n && (!exch[r] || !out[r])) rc = fail(err, XM_ERR_INVALID_ARG, "null peer pointer");
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            return launch_merge_p2p(exch, out, n, rank, world, unmatched, s, err);
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
 int32_t xm_clean_best_dev(const uint64_t* id, const uint64_t* rid, uint64_t n1, uint64_t n2, uint64_t* id1,
                           uint64_t* id2, uint64_t* lost, uint64_t* counts, int32_t device, void* stream,
                           char* errbuf, uint64_t errcap) {

@@ -80,6 +80,8 @@ int  calibrate_sin_model();   // probes the host libm: 1 = FMA Taylor model, 2 =
 // xm_index.cu
 int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
                     cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_merge_p2p(const void* const* exch, void* const* out, uint64_t n, int rank, int world,
+                         double unmatched, cudaStream_t s, Error& err);
 int32_t launch_merge_step(int which, unsigned long long* rid, double* rd, const double* ka, const double* kb,
                           double* key_out, uint64_t n, unsigned long long off, double unmatched,
                           cudaStream_t s, Error& err);

@@ -151,7 +151,53 @@ __global__ void merge_unpack_kernel(unsigned long long* __restrict__ rid, double
     rd[j] = ok ? kb[j] : unmatched;
 }
 
+// One-kernel reverse merge over NVLink peer memory: rank `rank` owns rows [lo, hi); for each it reads
+// every rank's raw (rd, rid) through the peer mappings, keeps the smallest distance -- the smallest
+// GLOBAL row id among equal distances (qxmatch.hpp:510-513) -- and stores the merged row into every
+// rank's result buffer. Loads and stores are coalesced 8-byte streams per peer.
+struct PeerSet {
+    const double* exch[XM_MAX_PEERS];       // n distances, n local row ids (uint64), first row of the rank (uint64)
+    double* out[XM_MAX_PEERS];              // n merged distances followed by n merged global ids
+};
+
+__global__ void __launch_bounds__(256)
+merge_p2p_kernel(PeerSet P, uint64_t n, uint64_t lo, uint64_t hi, int world, double unmatched) {
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x;
+    for (uint64_t j = lo + (uint64_t)blockIdx.x*blockDim.x + threadIdx.x; j < hi; j += stride) {
+        double bk = __longlong_as_double(0x7ff0000000000000ll);
+        unsigned long long br = kLost;
+#pragma unroll 4
+        for (int r = 0; r < world; ++r) {
+            const double k = P.exch[r][j];
+            const unsigned long long i = reinterpret_cast<const unsigned long long*>(P.exch[r])[n + j];
+            if (i == ~0ull) continue;
+            const unsigned long long gi = i + reinterpret_cast<const unsigned long long*>(P.exch[r])[2*n];
+            if (k < bk || (k == bk && gi < br)) { bk = k; br = gi; }
+        }
+        const bool ok = br != kLost;
+        const double od = ok ? bk : unmatched;
+        const unsigned long long oi = ok ? br : ~0ull;
+        for (int r = 0; r < world; ++r) {
+            P.out[r][j] = od;
+            reinterpret_cast<unsigned long long*>(P.out[r])[n + j] = oi;
+        }
+    }
+}
+
 }  // namespace
+
+int32_t launch_merge_p2p(const void* const* exch, void* const* out, uint64_t n, int rank, int world,
+                         double unmatched, cudaStream_t s, Error& err) {
+    PeerSet P;
+    for (int r = 0; r < world; ++r) { P.exch[r] = (const double*)exch[r]; P.out[r] = (double*)out[r]; }
+    const uint64_t lo = n*(uint64_t)rank/(uint64_t)world, hi = n*(uint64_t)(rank + 1)/(uint64_t)world;
+    if (hi == lo) return XM_OK;
+    uint64_t blocks = (hi - lo + 255)/256;
+    if (blocks > 148*8) blocks = 148*8;
+    merge_p2p_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, n, lo, hi, world, unmatched);
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
 
 int32_t launch_merge_step(int which, unsigned long long* rid, double* rd, const double* ka, const double* kb,
                           double* key_out, uint64_t n, unsigned long long off, double unmatched,

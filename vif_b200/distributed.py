@@ -42,9 +42,9 @@ def _cuda_bbox(ra, dec):
     return [out[0], out[1], out[2], out[3]]
 
 
-def _cuda_compute(ra1, dec1, ra2, dec2, params):
+def _cuda_compute(ra1, dec1, ra2, dec2, params, out=None):
     from .qxmatch import qxmatch
-    return qxmatch(ra1, dec1, ra2, dec2, params=params)
+    return qxmatch(ra1, dec1, ra2, dec2, params=params, out=out)
 
 
 def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=None, src=0,
@@ -91,7 +91,16 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     mark("bbox")
     p = QxmatchParams(**{**params.__dict__, "bbox1": (-ext[0], ext[1], -ext[2], ext[3])})
 
-    res = compute(ra1_local, dec1_local, ra2, dec2, p)
+    # the reverse results go straight into the peer-mapped exchange buffer of the merge when there is one
+    ent = None
+    if compute is _cuda_compute and world > 1 and not p.no_mirror:
+        ent = _p2p_buffers(ra2.numel(), ra2.device, world, group)
+    if ent is not None:
+        n2 = ra2.numel()
+        res = compute(ra1_local, dec1_local, ra2, dec2, p,
+                      out={"rd": ent[0][:n2], "rid": ent[0][n2:2*n2].view(torch.int64)})
+    else:
+        res = compute(ra1_local, dec1_local, ra2, dec2, p)
     mark("compute")
     ident, d, rid, rd = res.id, res.d, res.rid, res.rd
     if p.no_mirror:
@@ -100,7 +109,11 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     rid = torch.as_tensor(rid).view(torch.int64) if not isinstance(rid, torch.Tensor) else rid
     rd = torch.as_tensor(rd) if not isinstance(rd, torch.Tensor) else rd
     if rid.is_cuda:
-        _merge_reverse_cuda(rid, rd, int(row_offset), bool(p.linear), world, group)
+        merged = _merge_reverse_p2p(rid, rd, int(row_offset), bool(p.linear), world, group) if world > 1 else False
+        if merged:
+            rid, rd = merged
+        else:
+            _merge_reverse_cuda(rid, rd, int(row_offset), bool(p.linear), world, group)
     else:
         rid, rd = _merge_reverse_torch(rid, rd, int(row_offset), world, group)
     mark("merge")
@@ -170,6 +183,83 @@ def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, 
     p = QxmatchParams(**{**params.__dict__, "fwd_range": (int(row_offset), n_loc), "rev_range": (lo2, hi2 - lo2)})
     res = qxmatch(ra1, dec1, ra2, dec2, params=p)
     return res.id, res.d, res.rid, res.rd, (lo2, hi2)
+
+
+_P2P = {}           # (device, n, world, group) -> symmetric buffers of the peer-memory merge
+_P2P_OFF = set()    # groups on which symmetric memory could not be set up: NCCL merge from then on
+
+
+def _merge_reverse_p2p(rid, rd, row_offset, linear, world, group):
+    """Reverse merge as ONE kernel over NVLink peer memory (xm_rev_merge_p2p): every rank publishes
+    its (rd, rid, first row) in a symmetric buffer, merges its slice of the rows straight out of its
+    peers' memory and stores the result into every peer. torch's symmetric memory provides the peer
+    mappings and the two device-side barriers. Returns (rid, rd), or False when symmetric memory is
+    unavailable (the caller falls back to the NCCL all-reduce merge); XM_MERGE=nccl forces that."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    n = rid.numel()
+    dev = rid.device
+    ent = _p2p_buffers(n, dev, world, group)
+    if ent is None:
+        return False
+    exch, out, hx, ho, px, po, side = ent
+    lib = _lib.load()
+    err = C.create_string_buffer(512)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):        # a non-default stream: the library launches on the handle it is given
+        if rd.data_ptr() != exch.data_ptr():
+            exch[:n].copy_(rd)
+        if rid.data_ptr() != exch[n:].data_ptr():
+            exch[n:2*n].view(torch.int64).copy_(rid)
+        exch[2*n:].view(torch.int64).fill_(row_offset)
+        hx.barrier(channel=0)
+        rc = lib.xm_rev_merge_p2p(px, po, n, dist.get_rank(group), world, float("inf") if linear else float("nan"),
+                                  dev.index or 0, side.cuda_stream, err, 512)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        ho.barrier(channel=0)
+        res_rd = out[:n].clone()
+        res_rid = out[n:].view(torch.int64).clone()
+    cur.wait_stream(side)
+    return res_rid, res_rd
+
+
+def _p2p_buffers(n, dev, world, group):
+    """Symmetric (peer-mapped) buffers of the merge for n catalog-2 rows, created on first use --
+    a collective call. None when symmetric memory is unavailable or XM_MERGE=nccl."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    gkey = id(group) if group is not None else 0
+    if os.environ.get("XM_MERGE", "p2p") == "nccl" or gkey in _P2P_OFF or world > 16:
+        return None
+    key = (dev.index or 0, n, world, gkey)
+    ent = _P2P.get(key)
+    if ent is None:
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else dist.group.WORLD
+            exch = symm.empty(2*n + 1, dtype=torch.float64, device=dev)
+            out = symm.empty(2*n, dtype=torch.float64, device=dev)
+            hx, ho = symm.rendezvous(exch, g), symm.rendezvous(out, g)
+            px = (C.c_void_p*world)(*[int(q) for q in hx.buffer_ptrs])
+            po = (C.c_void_p*world)(*[int(q) for q in ho.buffer_ptrs])
+            ent = (exch, out, hx, ho, px, po, torch.cuda.Stream(device=dev))
+        except Exception as e:           # noqa: BLE001 -- any failure means "no peer mappings here"
+            if dist.get_rank(group) == 0:
+                print("[vif_b200] symmetric memory unavailable (%s): NCCL merge" % (str(e).splitlines() or ["?"])[0],
+                      flush=True)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+        if int(ok.item()) == 0:
+            _P2P_OFF.add(gkey)
+            return None
+        _P2P[key] = ent
+    return ent
 
 
 def _merge_reverse_cuda(rid, rd, row_offset, linear, world, group):

@@ -111,8 +111,9 @@ def release_memory(device=-1):
 
 def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, out=None, **kw):
     """See module docstring. `params` may be a QxmatchParams; keywords override its fields.
-    `out` (host path only): dict of preallocated numpy arrays id/d/rid/rd to receive the results,
-    e.g. views of pinned memory so that the D2H copies run at full PCIe rate."""
+    `out`: preallocated result buffers. Host path: dict of numpy arrays id/d/rid/rd, e.g. views of
+    pinned memory so that the D2H copies run at full PCIe rate. Device path: dict with CUDA tensors
+    for any of rid/rd (int64 / float64, n2 elements), e.g. views of a peer-mapped exchange buffer."""
     p = QxmatchParams(**{**(params.__dict__ if params is not None else {}), **kw})
     if ra2 is None and dec2 is None:
         # qxmatch.hpp:629-634: one catalog -> self match against itself
@@ -122,7 +123,7 @@ def qxmatch(ra1, dec1, ra2=None, dec2=None, params=None, out=None, **kw):
         raise TypeError("qxmatch: ra2 and dec2 must be given together")
     lib = _lib.load()
     if _is_torch_cuda(ra1):
-        return _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p)
+        return _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p, out)
     return _qxmatch_host(lib, ra1, dec1, ra2, dec2, p, out)
 
 
@@ -170,7 +171,7 @@ def _qxmatch_host(lib, ra1, dec1, ra2, dec2, p, out=None):
     return QxmatchRes(ident, d, rid, rd, last_stats(p.device))
 
 
-def _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p):
+def _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p, out=None):
     import torch
     for t in (ra1, dec1, ra2, dec2):
         if not (_is_torch_cuda(t) and t.dtype == torch.float64 and t.is_contiguous()):
@@ -185,8 +186,17 @@ def _qxmatch_torch(lib, ra1, dec1, ra2, dec2, p):
     n2o = int((p.rev_range or (0, 0))[1]) if ranged else n2
     ident = torch.empty((nth, n1o), dtype=torch.int64, device=dev)
     d = torch.empty((nth, n1o), dtype=torch.float64, device=dev)
-    rid = torch.empty(0 if p.no_mirror else n2o, dtype=torch.int64, device=dev)
-    rd = torch.empty(0 if p.no_mirror else n2o, dtype=torch.float64, device=dev)
+    nrev = 0 if p.no_mirror else n2o
+    rid = (out or {}).get("rid")
+    rd = (out or {}).get("rd")
+    for t, dt in ((rid, torch.int64), (rd, torch.float64)):
+        if t is not None and not (_is_torch_cuda(t) and t.dtype == dt and t.is_contiguous() and t.numel() == nrev
+                                  and t.device == dev):
+            raise TypeError("out['rid'] / out['rd'] must be contiguous CUDA int64 / float64 tensors of n2 elements")
+    if rid is None:
+        rid = torch.empty(nrev, dtype=torch.int64, device=dev)
+    if rd is None:
+        rd = torch.empty(nrev, dtype=torch.float64, device=dev)
     p.device = dev.index if dev.index is not None else torch.cuda.current_device()
     cp = p.to_c()
     err = C.create_string_buffer(1024)
