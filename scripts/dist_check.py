@@ -15,10 +15,12 @@ ok_all = True
 for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 100_000, 120_000, dict(nth=3)),
                          ("brute", 20_000, 15_000, dict(brute_force=True)), ("nomirror", 50_000, 50_000, dict(no_mirror=True)),
                          ("ties_across_shards", 100_000, 80_000, dict()), ("binned_nccl_merge", 300_000, 250_000, dict()),
-                         ("ties_nccl_merge", 100_000, 80_000, dict()), ("sparse_unmatched", 2_000, 50_000, dict())):
+                         ("ties_nccl_merge", 100_000, 80_000, dict()), ("sparse_unmatched", 2_000, 50_000, dict()),
+                         ("fullsky", 400_000, 300_000, dict())):
     os.environ["XM_MERGE"] = "nccl" if name.endswith("nccl_merge") else "p2p"
-    full1 = G.c2(1, n1, xp="torch", device=dev)
-    full2 = G.c2(2, n2, xp="torch", device=dev)
+    gen = G.fullsky if name == "fullsky" else G.c2
+    full1 = gen(1, n1, xp="torch", device=dev)
+    full2 = gen(2, n2, xp="torch", device=dev)
     if name.startswith("ties"):          # the two halves of catalog 1 are the same points: exact ties between ranks
         full1 = (torch.cat((full1[0][:n1//2], full1[0][:n1//2])), torch.cat((full1[1][:n1//2], full1[1][:n1//2])))
     lo, hi = shard_bounds(n1, world, rank)

@@ -301,6 +301,52 @@ def test_host_and_device_entries_agree():
         assert np.array_equal(getattr(h, k), dv[k], equal_nan=True)
 
 
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_rev_merge_p2p_kernel_on_one_device(world):
+    """xm_rev_merge_p2p with every "peer" buffer on this one GPU: each emulated rank merges its slice
+    and stores it into every result buffer; all must equal the rule of qxmatch.hpp:510-513 (smallest
+    distance, smallest global row among equal distances; unmatched stays NPOS / NaN)."""
+    import ctypes as C
+    lib = _lib.load()
+    n = 100_003
+    g = torch.Generator(device="cuda").manual_seed(11)
+    exch, outs, offs = [], [], []
+    for r in range(world):
+        rd = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        rd = (rd*8).floor()/8                                   # many exact ties between ranks
+        rid = torch.randint(0, 1000, (n,), dtype=torch.int64, device="cuda", generator=g)
+        lost = torch.rand(n, device="cuda", generator=g) < 0.3  # unmatched on this rank
+        rid[lost] = -1
+        rd[lost] = float("nan")
+        off = 1000*r
+        buf = torch.empty(2*n + 1, dtype=torch.float64, device="cuda")
+        buf[:n] = rd
+        buf[n:2*n].view(torch.int64).copy_(rid)
+        buf[2*n:].view(torch.int64).fill_(off)
+        exch.append(buf); offs.append(off)
+        outs.append(torch.full((2*n,), -7.0, dtype=torch.float64, device="cuda"))
+    torch.cuda.synchronize()
+    px = (C.c_void_p*world)(*[b.data_ptr() for b in exch])
+    po = (C.c_void_p*world)(*[b.data_ptr() for b in outs])
+    err = C.create_string_buffer(512)
+    for r in range(world):
+        rc = lib.xm_rev_merge_p2p(px, po, n, r, world, float("nan"), 0, None, err, 512)
+        assert rc == 0, err.value
+    torch.cuda.synchronize()             # device-wide: covers the library's own stream
+    big = torch.iinfo(torch.int64).max
+    key = torch.stack([torch.where(b[n:2*n].view(torch.int64) < 0, torch.full((n,), float("inf"), device="cuda", dtype=torch.float64), b[:n])
+                       for b in exch])
+    gid = torch.stack([torch.where(b[n:2*n].view(torch.int64) < 0, torch.full((n,), big, device="cuda"), b[n:2*n].view(torch.int64) + o)
+                       for b, o in zip(exch, offs)])
+    best = key.min(dim=0).values
+    exp_id = torch.where(key == best, gid, torch.full_like(gid, big)).min(dim=0).values
+    exp_rd = torch.where(exp_id == big, torch.full_like(best, float("nan")), best)
+    exp_id = torch.where(exp_id == big, torch.full_like(exp_id, -1), exp_id)
+    for o in outs:
+        assert torch.equal(o[n:].view(torch.int64), exp_id)
+        assert torch.equal(o[:n].nan_to_num(-1.0), exp_rd.nan_to_num(-1.0))
+
+
 def test_clean_best_device_matches_host():
     """xm_clean_best_dev (qxmatch.hpp:641-663 on the device) against the numpy restatement."""
     from vif_b200 import xmatch_clean_best
