@@ -61,13 +61,14 @@ def gen_catalog(G, config, seed, n, dev, start=0):
 
 # ---- clocks sampling --------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons read through NVML at a few points INSIDE the timed region
-    (synchronously, between steps: a polling thread or an `nvidia-smi -lms` child contends with the
-    CUDA driver and was measured to slow a 4 ms step by 40 %)."""
+    """SM clock + throttle reasons read through NVML at three points INSIDE the timed region, by a
+    helper thread woken for each read (a free-running polling thread or an `nvidia-smi -lms` child
+    contends with the CUDA driver and was measured to slow a 4 ms step by 40 %)."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.h, self.nv, self.max_mhz = gpu_index, [], None, None, 0.0
+        self.thread, self.wake, self.quit = None, None, False
 
     def start(self):
         try:
@@ -84,8 +85,28 @@ class ClockSampler:
             # the timed region; the per-sample queries (current clock, reasons) take microseconds
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.sample(keep=False)
+            # The queries run on a helper thread that sleeps until the timed loop asks for a sample:
+            # an NVML query is microseconds as a rule but was seen to block its caller for 7-30 ms
+            # (more often with several ranks inside the driver); the timed loop never waits for it.
+            import threading
+            self.wake = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
             self.nv = None
+
+    def _loop(self):
+        while True:
+            self.wake.wait()
+            self.wake.clear()
+            if self.quit:
+                return
+            self.sample()
+
+    def request(self):
+        """Asks the helper thread for one sample; returns at once."""
+        if self.wake is not None:
+            self.wake.set()
 
     def sample(self, keep=True):
         nv = self.nv
@@ -102,6 +123,10 @@ class ClockSampler:
             pass
 
     def stop(self):
+        if self.thread is not None:
+            self.quit = True
+            self.wake.set()
+            self.thread.join(timeout=2.0)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
         reasons = sorted(n for n, bit in self.REASONS.items() if any(r[2] & bit for r in self.rows))
@@ -250,19 +275,18 @@ def run_gpu_arm(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    # one rank's NVML query stalls for 4-13 ms when 8 processes share the driver (measured: the sampled
-    # steps of an 8-GPU run took 8-17 ms instead of 4.1): one sample in the middle there, three at N=1
-    sample_at = {args.steps // 2} if world > 1 else {0, args.steps // 2, max(args.steps - 2, 0)}
+    sample_at = {args.steps // 4, args.steps // 2, (3 * args.steps) // 4}      # clock samples inside the timed region
     e0.record()
     for k in range(args.steps):
+        if rank == 0 and k in sample_at:
+            sampler.request()               # read by the helper thread while this step runs on the GPU
         out = step(True)
         marks[k].record()
-        if rank == 0 and k in sample_at:
-            sampler.sample()
     e1.record()
     barrier()
     per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
-    args.step_ms = {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)}
+    args.step_ms = {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step),
+                    "argmax": int(np.argmax(per_step))}
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     launches = torch.tensor([stats_acc["launches"]], dtype=torch.float64, device=dev)
     if world > 1:

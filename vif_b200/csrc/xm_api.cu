@@ -51,6 +51,10 @@ struct Context {
     SearchCounters*     h_ctr = nullptr;     // pinned
     xm_stats     last;
     cudaEvent_t  ev[10];
+    // host-buffer calls: results leave over PCIe as soon as their lane is done (copy stream), the
+    // forward results while the reverse search is still running
+    cudaStream_t copy = nullptr;
+    struct HostOut { uint64_t* id = nullptr; double* d = nullptr; uint64_t* rid = nullptr; double* rd = nullptr; bool done = false; } host_out;
 };
 
 std::mutex g_mu;
@@ -70,8 +74,15 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     std::unique_ptr<Context> c(new Context);
     c->device = device;
     memset(&c->last, 0, sizeof(c->last));
-    XM_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    XM_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    // the forward lane gets the higher priority: its CTAs are dispatched first while both searches are
+    // in flight, so the forward results are complete (and on their way to the host) early
+    int prio_lo = 0, prio_hi = 0;
+    XM_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("XM_PRIORITY");
+    if (pe && pe[0] == '0') prio_hi = prio_lo;
+    XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+    XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->copy, cudaStreamNonBlocking, prio_hi));
     for (auto& e : c->sync_ev) XM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     XM_CUDA_TRY(cudaMalloc(&c->d_small, 16*sizeof(unsigned long long)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_small, 16*sizeof(unsigned long long)));
@@ -517,6 +528,12 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                                (uint32_t)n1o, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
         XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+        Context::HostOut& ho = ctx->host_out;
+        if (ho.id) {
+            XM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ev[6], 0));
+            XM_CUDA_TRY(cudaMemcpyAsync(ho.id, id, nth*n1o*8, cudaMemcpyDeviceToHost, ctx->copy));
+            XM_CUDA_TRY(cudaMemcpyAsync(ho.d, d, nth*n1o*8, cudaMemcpyDeviceToHost, ctx->copy));
+        }
         // ---- reverse search (lane s2) ----
         Scratch refine2, resrec2, plans2;
         XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
@@ -543,12 +560,21 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             }
         }
         XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
+        if (ho.id) {
+            if (mirror && n2o && ho.rid) {
+                XM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ev[7], 0));
+                XM_CUDA_TRY(cudaMemcpyAsync(ho.rid, rid, n2o*8, cudaMemcpyDeviceToHost, ctx->copy));
+                XM_CUDA_TRY(cudaMemcpyAsync(ho.rd, rd, n2o*8, cudaMemcpyDeviceToHost, ctx->copy));
+            }
+            ho.done = true;
+        }
         XM_CUDA_TRY(cudaEventRecord(sev[3], s2));
         XM_CUDA_TRY(cudaStreamWaitEvent(s, sev[3], 0));                // join
         XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(SearchCounters), cudaMemcpyDeviceToHost, s));
         XM_CUDA_TRY(cudaEventRecord(ev[8], s));
         XM_CUDA_TRY(cudaStreamSynchronize(s));
         XM_CUDA_TRY(cudaStreamSynchronize(s2));
+        if (ho.done) XM_CUDA_TRY(cudaStreamSynchronize(ctx->copy));
         st.ms_bbox = ev_ms(ev[0], ev[1]);
         st.ms_keys = ev_ms(ev[1], ev[2]);
         st.ms_sort = ev_ms(ev[2], ev[3]);
@@ -649,6 +675,7 @@ void xm_shutdown(void) {
         for (auto& e : c->ev) cudaEventDestroy(e);
         for (auto& e : c->sync_ev) cudaEventDestroy(e);
         cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2);
+        cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy);
         cudaFree(c->d_small); cudaFreeHost(c->h_small);
         cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr);
         cudaStreamDestroy(c->stream);
@@ -725,14 +752,20 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
         }
         XM_CUDA_TRY(did.alloc(nth*n1*8, s)); XM_CUDA_TRY(dd.alloc(nth*n1*8, s));
         if (mirror) { XM_CUDA_TRY(drid.alloc(n2*8, s)); XM_CUDA_TRY(drd.alloc(n2*8, s)); }
+        ctx->host_out.id = id; ctx->host_out.d = d; ctx->host_out.rid = mirror ? rid : nullptr;
+        ctx->host_out.rd = mirror ? rd : nullptr; ctx->host_out.done = false;
         int32_t r = run_device(ctx, s, dra1.as<double>(), ddec1.as<double>(), n1, pra2, pdec2, n2, *params,
                                did.as<uint64_t>(), dd.as<double>(), drid.as<uint64_t>(), drd.as<double>(), err);
-        if (r) return r;
-        XM_CUDA_TRY(cudaMemcpyAsync(id, did.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
-        XM_CUDA_TRY(cudaMemcpyAsync(d, dd.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
-        if (mirror) {
-            XM_CUDA_TRY(cudaMemcpyAsync(rid, drid.p, n2*8, cudaMemcpyDeviceToHost, s));
-            XM_CUDA_TRY(cudaMemcpyAsync(rd, drd.p, n2*8, cudaMemcpyDeviceToHost, s));
+        const bool copied = ctx->host_out.done;      // the cell-binned path ships results lane by lane
+        ctx->host_out = Context::HostOut();
+        if (r) { cudaStreamSynchronize(ctx->copy); return r; }
+        if (!copied) {
+            XM_CUDA_TRY(cudaMemcpyAsync(id, did.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
+            XM_CUDA_TRY(cudaMemcpyAsync(d, dd.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
+            if (mirror) {
+                XM_CUDA_TRY(cudaMemcpyAsync(rid, drid.p, n2*8, cudaMemcpyDeviceToHost, s));
+                XM_CUDA_TRY(cudaMemcpyAsync(rd, drd.p, n2*8, cudaMemcpyDeviceToHost, s));
+            }
         }
         XM_CUDA_TRY(cudaStreamSynchronize(s));
         ctx->last.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
