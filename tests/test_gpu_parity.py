@@ -301,6 +301,28 @@ def test_host_and_device_entries_agree():
         assert np.array_equal(getattr(h, k), dv[k], equal_nan=True)
 
 
+def test_pageable_host_buffers_go_through_staging_pipeline():
+    """Host-buffer call on ordinary numpy arrays large enough to wrap the staging ring several times
+    (xm_staging.cu: 12 x 4 MB bounce buffers): results must equal the device-buffer call, and the
+    pinned-buffer call (direct DMA + lane-by-lane result copies) as well."""
+    n1, n2 = 3_000_017, 2_500_003
+    ra1, dec1 = G.c2(81, n1)
+    ra2, dec2 = G.c2(82, n2)
+    dev = qxmatch(*(torch.from_numpy(a).cuda() for a in (ra1, dec1, ra2, dec2)))
+    host = qxmatch(ra1, dec1, ra2, dec2)
+    pin = [torch.from_numpy(a).pin_memory() for a in (ra1, dec1, ra2, dec2)]
+    out = {"id": torch.empty((1, n1), dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+           "d": torch.empty((1, n1), dtype=torch.float64).pin_memory().numpy(),
+           "rid": torch.empty(n2, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+           "rd": torch.empty(n2, dtype=torch.float64).pin_memory().numpy()}
+    pinned = qxmatch(*(t.numpy() for t in pin), out=out)
+    for r in (host, pinned):
+        assert np.array_equal(r.id, dev.id.cpu().numpy().view(np.uint64))
+        assert np.array_equal(r.d, dev.d.cpu().numpy())
+        assert np.array_equal(r.rid, dev.rid.cpu().numpy().view(np.uint64))
+        assert np.array_equal(r.rd, dev.rd.cpu().numpy())
+
+
 @pytest.mark.parametrize("world", [1, 2, 5])
 def test_rev_merge_p2p_kernel_on_one_device(world):
     """xm_rev_merge_p2p with every "peer" buffer on this one GPU: each emulated rank merges its slice

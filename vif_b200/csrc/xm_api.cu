@@ -681,6 +681,7 @@ void xm_shutdown(void) {
         cudaStreamDestroy(c->stream);
     }
     g_ctx.clear();
+    stage_shutdown();
 }
 
 int32_t xm_release_memory(int32_t device) {
@@ -741,31 +742,50 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
         const bool same_cat = (ra1 == ra2 && dec1 == dec2 && n1 == n2);
         Scratch dra1, ddec1, dra2, ddec2, did, dd, drid, drd;
         XM_CUDA_TRY(dra1.alloc(n1*8, s)); XM_CUDA_TRY(ddec1.alloc(n1*8, s));
-        XM_CUDA_TRY(cudaMemcpyAsync(dra1.p, ra1, n1*8, cudaMemcpyHostToDevice, s));
-        XM_CUDA_TRY(cudaMemcpyAsync(ddec1.p, dec1, n1*8, cudaMemcpyHostToDevice, s));
         const double *pra2 = dra1.as<double>(), *pdec2 = ddec1.as<double>();
         if (!same_cat) {
             XM_CUDA_TRY(dra2.alloc(n2*8, s)); XM_CUDA_TRY(ddec2.alloc(n2*8, s));
-            XM_CUDA_TRY(cudaMemcpyAsync(dra2.p, ra2, n2*8, cudaMemcpyHostToDevice, s));
-            XM_CUDA_TRY(cudaMemcpyAsync(ddec2.p, dec2, n2*8, cudaMemcpyHostToDevice, s));
             pra2 = dra2.as<double>(); pdec2 = ddec2.as<double>();
+        }
+        // inputs: pinned buffers go straight to the DMA engine, pageable ones (std::vector storage
+        // behind the drop-in header) through the chunked staging pipeline of xm_staging.cu
+        {
+            StageJob in[4] = {{dra1.p, (void*)ra1, (size_t)n1*8}, {ddec1.p, (void*)dec1, (size_t)n1*8},
+                              {dra2.p, (void*)ra2, (size_t)n2*8}, {ddec2.p, (void*)dec2, (size_t)n2*8}};
+            StageJob staged[4];
+            int ns = 0;
+            for (int k = 0; k < (same_cat ? 2 : 4); ++k) {
+                if (in[k].bytes == 0) continue;
+                if (host_pointer_is_pageable(in[k].host)) staged[ns++] = in[k];
+                else XM_CUDA_TRY(cudaMemcpyAsync(in[k].dev, in[k].host, in[k].bytes, cudaMemcpyHostToDevice, s));
+            }
+            if (ns) { int32_t r = stage_h2d(ctx->device, staged, ns, s, err); if (r) return r; }
         }
         XM_CUDA_TRY(did.alloc(nth*n1*8, s)); XM_CUDA_TRY(dd.alloc(nth*n1*8, s));
         if (mirror) { XM_CUDA_TRY(drid.alloc(n2*8, s)); XM_CUDA_TRY(drd.alloc(n2*8, s)); }
-        ctx->host_out.id = id; ctx->host_out.d = d; ctx->host_out.rid = mirror ? rid : nullptr;
-        ctx->host_out.rd = mirror ? rd : nullptr; ctx->host_out.done = false;
+        StageJob outj[4] = {{did.p, id, (size_t)(nth*n1*8)}, {dd.p, d, (size_t)(nth*n1*8)},
+                            {drid.p, rid, mirror ? (size_t)n2*8 : 0}, {drd.p, rd, mirror ? (size_t)n2*8 : 0}};
+        bool out_pinned = true;
+        for (int k = 0; k < 4; ++k) if (outj[k].bytes && host_pointer_is_pageable(outj[k].host)) out_pinned = false;
+        if (out_pinned) {       // results leave lane by lane from inside the cell-binned pipeline
+            ctx->host_out.id = id; ctx->host_out.d = d; ctx->host_out.rid = mirror ? rid : nullptr;
+            ctx->host_out.rd = mirror ? rd : nullptr;
+        }
+        ctx->host_out.done = false;
         int32_t r = run_device(ctx, s, dra1.as<double>(), ddec1.as<double>(), n1, pra2, pdec2, n2, *params,
                                did.as<uint64_t>(), dd.as<double>(), drid.as<uint64_t>(), drd.as<double>(), err);
-        const bool copied = ctx->host_out.done;      // the cell-binned path ships results lane by lane
+        const bool copied = ctx->host_out.done;
         ctx->host_out = Context::HostOut();
         if (r) { cudaStreamSynchronize(ctx->copy); return r; }
         if (!copied) {
-            XM_CUDA_TRY(cudaMemcpyAsync(id, did.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
-            XM_CUDA_TRY(cudaMemcpyAsync(d, dd.p, nth*n1*8, cudaMemcpyDeviceToHost, s));
-            if (mirror) {
-                XM_CUDA_TRY(cudaMemcpyAsync(rid, drid.p, n2*8, cudaMemcpyDeviceToHost, s));
-                XM_CUDA_TRY(cudaMemcpyAsync(rd, drd.p, n2*8, cudaMemcpyDeviceToHost, s));
+            StageJob staged[4];
+            int ns = 0;
+            for (int k = 0; k < 4; ++k) {
+                if (outj[k].bytes == 0) continue;
+                if (host_pointer_is_pageable(outj[k].host)) staged[ns++] = outj[k];
+                else XM_CUDA_TRY(cudaMemcpyAsync(outj[k].host, outj[k].dev, outj[k].bytes, cudaMemcpyDeviceToHost, s));
             }
+            if (ns) { int32_t r2 = stage_d2h(ctx->device, staged, ns, s, err); if (r2) return r2; }
         }
         XM_CUDA_TRY(cudaStreamSynchronize(s));
         ctx->last.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

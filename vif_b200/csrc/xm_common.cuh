@@ -80,6 +80,13 @@ int  calibrate_sin_model();   // probes the host libm: 1 = FMA Taylor model, 2 =
 // xm_index.cu
 int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
                     cudaStream_t s, Error& err, uint64_t* launches);
+// pageable host buffers (xm_staging.cu)
+struct StageJob { void* dev; void* host; size_t bytes; };
+bool    host_pointer_is_pageable(const void* p);
+int32_t stage_h2d(int device, const StageJob* jobs, int njobs, cudaStream_t s, Error& err);
+int32_t stage_d2h(int device, const StageJob* jobs, int njobs, cudaStream_t s, Error& err);
+void    stage_shutdown();
+
 int32_t launch_merge_p2p(const void* const* exch, void* const* out, uint64_t n, int rank, int world,
                          double unmatched, cudaStream_t s, Error& err);
 int32_t launch_merge_step(int which, unsigned long long* rid, double* rd, const double* ka, const double* kb,
