@@ -54,6 +54,8 @@ struct Context {
     // host-buffer calls: results leave over PCIe as soon as their lane is done (copy stream), the
     // forward results while the reverse search is still running
     cudaStream_t copy = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};   // exact kernel of the undecided rows, one per lane
+    cudaEvent_t  lane_ev[4];
     struct HostOut { uint64_t* id = nullptr; double* d = nullptr; uint64_t* rid = nullptr; double* rd = nullptr; bool done = false; } host_out;
 };
 
@@ -83,6 +85,9 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
     XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->copy, cudaStreamNonBlocking, prio_hi));
+    XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->side[0], cudaStreamNonBlocking, prio_hi));
+    XM_CUDA_TRY(cudaStreamCreateWithPriority(&c->side[1], cudaStreamNonBlocking, prio_lo));
+    for (auto& e : c->lane_ev) XM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->sync_ev) XM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     XM_CUDA_TRY(cudaMalloc(&c->d_small, 16*sizeof(unsigned long long)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_small, 16*sizeof(unsigned long long)));
@@ -510,11 +515,16 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
             XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1o), s));
             XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
+            // filter -> (unpack on s || exact kernel of the undecided rows on a side stream) -> join
             if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
-                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, err, &launches))) return rc;
+                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
+                                            &launches))) return rc;
+            XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[0], ctx->lane_ev[0], 0));
             if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
-                                               (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr, s,
-                                               err, &launches))) return rc;
+                                               (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr,
+                                               ctx->side[0], err, &launches))) return rc;
+            XM_CUDA_TRY(cudaEventRecord(ctx->lane_ev[1], ctx->side[0]));
+            XM_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_ev[1], 0));
         } else if (!P.exact_only && fast_path_applicable(g) && topk_filter_applicable(nth_eff)) {
             // nth = 2..8: top-K filter kernel, exact kernel on the rows it flags (cells are in row order)
             XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
@@ -545,11 +555,14 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                     XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
                     if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,
                                                     refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
-                                                    s2, err, &launches))) return rc;
+                                                    s2, ctx->lane_ev[2], err, &launches))) return rc;
+                    XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[1], ctx->lane_ev[2], 0));
                     if ((rc = launch_ring_search_exact(g, *srcR, s1.view, 0, 1u, n2o, rid, rd,
                                                        refine2.as<uint32_t>(), (uint32_t)n2o,
-                                                       &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr, s2, err,
-                                                       &launches))) return rc;
+                                                       &ctx->d_ctr->refine_rev, true, unordered, ctx->d_ctr,
+                                                       ctx->side[1], err, &launches))) return rc;
+                    XM_CUDA_TRY(cudaEventRecord(ctx->lane_ev[3], ctx->side[1]));
+                    XM_CUDA_TRY(cudaStreamWaitEvent(s2, ctx->lane_ev[3], 0));
                 } else {
                     if ((rc = launch_ring_search_exact(g, *srcR, s1.view, 0, 1u, n2o, rid, rd, nullptr,
                                                        (uint32_t)n2o, nullptr, true, false, ctx->d_ctr, s2, err, &launches))) return rc;
@@ -676,6 +689,8 @@ void xm_shutdown(void) {
         for (auto& e : c->sync_ev) cudaEventDestroy(e);
         cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2);
         cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy);
+        for (auto& q : c->side) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
+        for (auto& e : c->lane_ev) cudaEventDestroy(e);
         cudaFree(c->d_small); cudaFreeHost(c->h_small);
         cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr);
         cudaStreamDestroy(c->stream);

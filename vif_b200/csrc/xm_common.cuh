@@ -134,7 +134,8 @@ size_t  filter_plan_bytes(uint64_t n);       // scratch for the per-tile staging
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
-                              SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches);
+                              SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
+                              uint64_t* launches);
 int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1, const double* c1,
                            uint32_t n1, const double* x2, const double* y2, const double* c2,
                            uint32_t n2, bool self, uint32_t nth_eff, uint64_t plane_stride,

@@ -27,6 +27,9 @@ __device__ __forceinline__ Rec load_rec(const Rec* p) {
 // result of one source, padded to a DRAM sector (a scattered 8-byte store costs a read-modify-write
 // of the sector); unpack_results_kernel splits the records into id[] / d[] with coalesced accesses
 struct __align__(32) ResRec { uint64_t id; double d; uint64_t pad0, pad1; };
+// record of a row the filter could not decide: the unpack pass leaves such rows alone, so that the
+// exact kernel can write them while the unpack pass is still running (no catalog has 2^64 - 2 rows)
+constexpr uint64_t kUndecidedId = 0xfffffffffffffffeull;
 
 __device__ __forceinline__ void store_res(ResRec* p, uint64_t id, double d) {
     asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%3};" :: "l"(p), "l"(id), "l"(__double_as_longlong(d)), "l"(0ll) : "memory");

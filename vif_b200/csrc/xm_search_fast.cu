@@ -400,6 +400,7 @@ ring_nn_filter_kernel(GridView g, CatView src, CatView cand, const TilePlan* __r
         if (flag) {
             const unsigned long long pos = atomicAdd(refine_count, 1ull);
             refine_list[pos] = p;
+            store_res(res + me.idx, kUndecidedId, 0.0);
         } else {
             // exact proxy of the winning pair in reference-order arithmetic -> arcsec
             const Rec w = load_rec(cand.rec + b.slot);
@@ -421,6 +422,7 @@ unpack_results_kernel(const ResRec* __restrict__ res, uint32_t n, uint64_t* __re
     if (i >= n) return;
     unsigned long long a, b, c, d;
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(res + i));
+    if (a == kUndecidedId) return;          // the exact kernel owns this row
     id_out[i] = a;
     d_out[i] = __longlong_as_double((long long)b);
 }
@@ -452,7 +454,8 @@ bool fast_path_applicable(const GridView& g) {
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
-                              SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches) {
+                              SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
+                              uint64_t* launches) {
     if (src.n == 0) return XM_OK;
     const uint32_t ntiles = (src.n + kThreads - 1)/kThreads;
     ResRec* res = (ResRec*)result_scratch;
@@ -467,7 +470,9 @@ int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatVi
         g, src, cand, plan, res, refine_list, refine_count, reverse ? 1 : 0, ctr);
     else ring_nn_filter_kernel<false><<<ntiles, kThreads, sizeof(FilterSmem), s>>>(
         g, src, cand, plan, res, refine_list, refine_count, reverse ? 1 : 0, ctr);
-    // rows flagged for the exact kernel carry garbage here; it overwrites them afterwards
+    // the list of undecided rows is complete here: the caller starts the exact kernel on a side
+    // stream from this event, concurrently with the unpack pass (which skips those rows)
+    if (filter_done) XM_CUDA_TRY(cudaEventRecord(filter_done, s));
     unpack_results_kernel<<<(src.n + 255)/256, 256, 0, s>>>(res, src.n, id_out, d_out);
     *launches += 3;
     XM_CUDA_TRY(cudaGetLastError());

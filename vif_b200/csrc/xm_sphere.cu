@@ -275,6 +275,7 @@ sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo,
         if (flag) {
             const unsigned long long pos = atomicAdd(refine_count, 1ull);
             refine_list[pos] = p;
+            if (res) store_res(res + me.idx, filt::kUndecidedId, 0.0);
         } else {
             const double dist = proxy_to_true_small(proxy_sph_small(x1, y1, c1, w.x, w.y, w.c, g.sin_model));
             if (res) store_res(res + me.idx, (uint64_t)w.idx, dist);
