@@ -241,14 +241,16 @@ int32_t run_sphere(Context* ctx, cudaStream_t s, const double* ra1, const double
     XM_CUDA_TRY(rl1.alloc((size_t)n1*4, s));
     if (nth == 1 && rr1.alloc(filter_result_bytes(n1), s) != cudaSuccess) { cudaGetLastError(); rr1.p = nullptr; }
     if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), s1.view, *v2, self, nth, n1, id, d, rl1.as<uint32_t>(),
-                                   &ctx->d_ctr->refine_fwd, rr1.p, false, ctx->d_ctr, s, err, launches))) return rc;
+                                   &ctx->d_ctr->refine_fwd, rr1.p, false, ctx->d_ctr, s, ctx->side[0], ctx->lane_ev[0],
+                                   ctx->lane_ev[1], err, launches))) return rc;
     XM_CUDA_TRY(cudaEventRecord(ev[6], s));
     XM_CUDA_TRY(cudaEventRecord(ev[9], s2));
     if (mirror) {
         XM_CUDA_TRY(rl2.alloc((size_t)n2*4, s2));
         if (rr2.alloc(filter_result_bytes(n2), s2) != cudaSuccess) { cudaGetLastError(); rr2.p = nullptr; }
         if ((rc = launch_sphere_search(g, wrap, cmin.as<double>(), *v2, s1.view, self, 1u, n2, rid, rd, rl2.as<uint32_t>(),
-                                       &ctx->d_ctr->refine_rev, rr2.p, true, ctx->d_ctr, s2, err, launches))) return rc;
+                                       &ctx->d_ctr->refine_rev, rr2.p, true, ctx->d_ctr, s2, ctx->side[1],
+                                       ctx->lane_ev[2], ctx->lane_ev[3], err, launches))) return rc;
     }
     XM_CUDA_TRY(cudaEventRecord(ev[7], s2));
     XM_CUDA_TRY(cudaEventRecord(sev[3], s2));

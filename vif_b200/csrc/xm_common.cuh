@@ -167,7 +167,8 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
                              const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
                              uint64_t* id_out, double* d_out, uint32_t* refine_list,
                              unsigned long long* refine_count, void* result_records, bool reverse,
-                             SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches);
+                             SearchCounters* ctr, cudaStream_t s, cudaStream_t side, cudaEvent_t ev_fork,
+                             cudaEvent_t ev_join, Error& err, uint64_t* launches);
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
                              uint64_t* launches);

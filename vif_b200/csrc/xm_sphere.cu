@@ -351,7 +351,8 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
                              const CatView& cand, bool self, uint32_t nth_eff, uint64_t plane_stride,
                              uint64_t* id_out, double* d_out, uint32_t* refine_list,
                              unsigned long long* refine_count, void* result_records, bool reverse,
-                             SearchCounters* ctr, cudaStream_t s, Error& err, uint64_t* launches) {
+                             SearchCounters* ctr, cudaStream_t s, cudaStream_t side, cudaEvent_t ev_fork,
+                             cudaEvent_t ev_join, Error& err, uint64_t* launches) {
     if (src.n == 0 || nth_eff == 0) return XM_OK;
     SphereGrid sg;
     sg.g = g; sg.wrap = wrap; sg.cmin_row = cmin_row;
@@ -371,18 +372,35 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
         else { if (wrap) XM_FILT(false, true); else XM_FILT(false, false); }
 #undef XM_FILT
         XM_CUDA_TRY(cudaGetLastError());
-        // rows flagged for the exact kernel carry garbage in their records; it overwrites them afterwards
-        if (res) { int32_t rc = launch_unpack_results(res, src.n, id_out, d_out, s, err, launches); if (rc) return rc; }
         *launches += 1;
         rows = refine_list;
         if (grid.x > 148*8) grid.x = 148*8;
+        if (res) {
+            // the unpack pass skips the undecided rows (kUndecidedId), so the exact kernel can write
+            // them from a side stream while it runs
+            if (side) {
+                XM_CUDA_TRY(cudaEventRecord(ev_fork, s));
+                XM_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+            }
+            int32_t rc = launch_unpack_results(res, src.n, id_out, d_out, s, err, launches);
+            if (rc) return rc;
+        } else {
+            side = nullptr;       // rows were written in place by the filter: keep the order
+        }
+    } else {
+        side = nullptr;
     }
-#define XM_CASE(KK) case KK: sphere_search_kernel<KK><<<grid, kThreads, 0, s>>>(sg, src, cand, self ? 1 : 0, \
+    cudaStream_t sx = side ? side : s;
+#define XM_CASE(KK) case KK: sphere_search_kernel<KK><<<grid, kThreads, 0, sx>>>(sg, src, cand, self ? 1 : 0, \
         nth_eff, plane_stride, id_out, d_out, rows, refine_count, reverse ? 1 : 0, ctr); break;
     switch (nth_eff) { XM_CASE(1) XM_CASE(2) XM_CASE(3) XM_CASE(4) XM_CASE(5) XM_CASE(6) XM_CASE(7) default: XM_CASE(8) }
 #undef XM_CASE
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
+    if (side) {
+        XM_CUDA_TRY(cudaEventRecord(ev_join, side));
+        XM_CUDA_TRY(cudaStreamWaitEvent(s, ev_join, 0));
+    }
     return XM_OK;
 }
 
