@@ -203,7 +203,7 @@ constexpr uint32_t pack9(int a0, int a1, int a2, int a3, int a4, int a5, int a6,
 constexpr uint32_t kNbX = pack9(0, 0, 0, 1, -1, 1, -1, 1, -1);
 constexpr uint32_t kNbY = pack9(0, 1, -1, 0, 0, 1, 1, -1, -1);
 
-template <bool SELF, bool WRAP>
+template <bool SELF>
 __global__ void __launch_bounds__(kThreads)
 sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo, ResRec* __restrict__ res,
                         uint64_t* __restrict__ id_out, double* __restrict__ d_out,
@@ -211,50 +211,90 @@ sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo,
                         SearchCounters* ctr) {
     const GridView& g = sg.g;
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
+    const bool live = p < src.n;
     uint32_t evals = 0;
-    if (p < src.n) {
-        const Rec me = filt::load_rec(src.rec + p);
-        const double x1 = me.x, y1 = me.y, c1 = me.c;
-        const int ncol = (int)g.nra, nrow = (int)g.ndec;
-        const int x0 = (int)(me.key/g.ndec), y0 = (int)(me.key - (uint32_t)x0*g.ndec);
-        const double wx = g.wx, wy = g.wy;
-        bool flag = !(c1 >= 0.0) || y0 < 1 || y0 + 1 >= nrow || (!WRAP && (x0 < 1 || x0 + 1 >= ncol));
-        int32_t h1 = kInfHi, h2 = kInfHi;
-        uint32_t slot = kNone;
-        if (!flag) {
-            // key offsets of the east / west columns (modulo the circle in wrap mode)
-            int32_t de = (int32_t)g.ndec, dw = -(int32_t)g.ndec;
-            if (WRAP) { if (x0 + 1 >= ncol) de -= (int32_t)(g.ndec*g.nra); if (x0 < 1) dw += (int32_t)(g.ndec*g.nra); }
-            const double cx_lo = g.ox + (double)x0*wx, cy_lo = g.oy + (double)y0*wy;
-            double ge = cx_lo + wx - x1 - g.fzx, gw = x1 - cx_lo - g.fzx;
-            double gn = cy_lo + wy - y1 - g.fzy, gs = y1 - cy_lo - g.fzy;
-            ge = ge > 0 ? ge : 0; gw = gw > 0 ? gw : 0; gn = gn > 0 ? gn : 0; gs = gs > 0 ? gs : 0;
-            const double shrink = 1.0 - eps_lo - 1e-9;
-            const double cm0 = sg.cmin_row[y0]*c1, cmn = sg.cmin_row[y0 + 1]*c1, cms = sg.cmin_row[y0 - 1]*c1;
-#pragma unroll 1
-            for (int e = 0; e < 9; ++e) {
+    Rec me;
+    me.x = me.y = 0.0; me.c = -1.0; me.idx = 0; me.key = 0;
+    if (live) me = filt::load_rec(src.rec + p);
+    const double x1 = me.x, y1 = me.y, c1 = me.c;
+    const int ncol = (int)g.nra, nrow = (int)g.ndec;
+    const int x0 = (int)(me.key/g.ndec), y0 = (int)(me.key - (uint32_t)x0*g.ndec);
+    const double wx = g.wx, wy = g.wy;
+    // grid edge, polar rows and the columns next to the RA seam (dx would need wrapping) are the
+    // exact kernel's: 2/ncol of the sources on a full-sky grid
+    bool flag = !(c1 >= 0.0) || y0 < 1 || y0 + 1 >= nrow || x0 < 1 || x0 + 1 >= ncol;
+    int32_t h1 = kInfHi, h2 = kInfHi;
+    uint32_t slot = kNone;
+    double ge = 0, gw = 0, gn = 0, gs = 0, cm0 = 0, cmn = 0, cms = 0;
+    const double shrink = 1.0 - eps_lo - 1e-9;
+    uint32_t q = 0, qe = 0;
+
+#define XM_EVAL()                                                                   \
+    {                                                                               \
+        const Rec cd = filt::load_rec(cand.rec + q);                                \
+        const double dx = cd.x - x1, dy = cd.y - y1;                                \
+        int32_t h = __double2hiint(fma(dx*dx*cd.c, c1, dy*dy));                     \
+        if (SELF && cd.idx == me.idx) h = kInfHi;                                   \
+        const bool better = h < h1;                                                 \
+        h2 = min(h2, max(h1, h));                                                   \
+        h1 = min(h1, h);                                                            \
+        slot = better ? q : slot;                                                   \
+        ++q;                                                                        \
+    }
+
+    // ---- A. own cell, lanes in lockstep ----------------------------------------------------------------
+    if (!flag) {
+        const double cx_lo = g.ox + (double)x0*wx, cy_lo = g.oy + (double)y0*wy;
+        ge = cx_lo + wx - x1 - g.fzx; gw = x1 - cx_lo - g.fzx;
+        gn = cy_lo + wy - y1 - g.fzy; gs = y1 - cy_lo - g.fzy;
+        ge = ge > 0 ? ge : 0; gw = gw > 0 ? gw : 0; gn = gn > 0 ? gn : 0; gs = gs > 0 ? gs : 0;
+        cm0 = sg.cmin_row[y0]*c1; cmn = sg.cmin_row[y0 + 1]*c1; cms = sg.cmin_row[y0 - 1]*c1;
+        q = cand.cstart[me.key]; qe = cand.cstart[me.key + 1];
+        evals += qe - q;
+        while (q < qe) XM_EVAL()
+    }
+    // ---- B. which of the eight neighbours can hold a winner or a near-tie? (all lanes together) ---------
+    uint32_t todo = 0;
+    if (!flag) {
+        const double thr = hi_ceil(h1)*(1.0 + 1e-9);
+        const double Qe = ge*ge, Qw = gw*gw, Qn = gn*gn*shrink, Qs = gs*gs*shrink;
+        const double s0 = cm0*shrink, sn = cmn*shrink, ss = cms*shrink;
+        // bit e of kNbX/kNbY order: 1 N, 2 S, 3 E, 4 W, 5 NE, 6 NW, 7 SE, 8 SW
+        todo = (Qn < thr ? 2u : 0u) | (Qs < thr ? 4u : 0u) | (Qe*s0 < thr ? 8u : 0u) | (Qw*s0 < thr ? 16u : 0u) |
+               (fma(Qe, sn, Qn) < thr ? 32u : 0u) | (fma(Qw, sn, Qn) < thr ? 64u : 0u) |
+               (fma(Qe, ss, Qs) < thr ? 128u : 0u) | (fma(Qw, ss, Qs) < thr ? 256u : 0u);
+    }
+    // ---- C. one flat loop over the candidates of the surviving neighbours ------------------------------
+    // A lane moves on to its next cell on its own, so the warp runs for the longest lane's total, not
+    // for the sum of the per-cell maxima (walking the nine cells in lockstep kept 7.8 of 32 lanes busy).
+    // Every lane of the warp stays in the loop until the last one is done: the pop branch and the
+    // evaluation reconverge each iteration.
+    bool active = todo != 0;
+    q = qe = 0;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active && q == qe) {
+            bool found = false;
+            while (todo) {
+                const int e = __ffs(todo) - 1;
+                todo &= todo - 1;
                 const int bx = (int)((kNbX >> (2*e)) & 3u) - 1, by = (int)((kNbY >> (2*e)) & 3u) - 1;
                 const double gx = bx > 0 ? ge : (bx < 0 ? gw : 0.0), gy = by > 0 ? gn : (by < 0 ? gs : 0.0);
                 const double cm = by > 0 ? cmn : (by < 0 ? cms : cm0);
-                // lower bound (in Q) of the cell's candidates against the current best
-                const double lb = fma(gx*gx, cm, gy*gy)*shrink;
-                if (e > 0 && !(lb < hi_ceil(h1)*(1.0 + 1e-9))) continue;
-                const uint32_t k = me.key + (uint32_t)(bx > 0 ? de : (bx < 0 ? dw : 0)) + (uint32_t)by;
-                const uint32_t qs = cand.cstart[k], qe = cand.cstart[k + 1];
-                for (uint32_t q = qs; q < qe; ++q) {
-                    const Rec cd = filt::load_rec(cand.rec + q);
-                    double dx = cd.x - x1;
-                    const double dy = cd.y - y1;
-                    if (WRAP) dx = dx > 3.141592653589793 ? dx - 6.283185307179586 : (dx < -3.141592653589793 ? dx + 6.283185307179586 : dx);
-                    int32_t h = __double2hiint(fma(dx*dx*cd.c, c1, dy*dy));
-                    if (SELF && cd.idx == me.idx) h = kInfHi;
-                    const bool better = h < h1;
-                    h2 = min(h2, max(h1, h));
-                    h1 = min(h1, h);
-                    slot = better ? q : slot;
-                }
-                evals += qe - qs;
+                // the best may have improved since step B
+                if (!(fma(gx*gx, cm, gy*gy)*shrink < hi_ceil(h1)*(1.0 + 1e-9))) continue;
+                const uint32_t k = me.key + (uint32_t)(bx*(int32_t)g.ndec + by);
+                q = cand.cstart[k]; qe = cand.cstart[k + 1];
+                evals += qe - q;
+                if (q != qe) { found = true; break; }
             }
+            active = found;
+        }
+        if (active) XM_EVAL()
+    }
+#undef XM_EVAL
+
+    if (live) {
+        if (!flag) {
             // (1) completeness: proxy bounds of everything outside the 3x3 block, with
             // sin^2 h >= h^2 (1 - h^2/3) for every h; (2) winner vs runner-up
             const double oy = wy - 2.0*g.fzy, ox = wx - 2.0*g.fzx;      // binning slack of the far cells
@@ -269,7 +309,7 @@ sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo,
         Rec w;
         if (!flag) {
             w = filt::load_rec(cand.rec + slot);
-            // the small-angle sine covers |dx|/2 < 0.126; pairs across the RA seam go to the exact kernel
+            // the small-angle sine covers |dx|/2 < 0.126
             if (!(fabs(w.x - x1) < 0.25 && fabs(w.y - y1) < 0.25)) flag = true;
         }
         if (flag) {
@@ -316,7 +356,9 @@ bool sphere_grid(const double* bb, uint64_t n_cand, uint32_t nth, GridView* g, i
     const double span = *wrap ? 360.0 : fmax(ra1 - ra0, 1e-9);
     // solid angle of the box and a cell size aiming at ~8*nth candidates per cell
     const double omega = (span*pi/180.0)*fmax(sin(de1*pi/180.0) - sin(de0*pi/180.0), 1e-12);
-    double h = sqrt(omega*8.0*(double)(nth ? nth : 1)/(double)(n_cand ? n_cand : 1))*180.0/pi;   // [deg]
+    const char* dens = getenv("XM_SPHERE_DENSITY");
+    const double per_cell = dens ? atof(dens) : 8.0;    // measured on C5 (1e9 x 1e8): 8 -> 204 ms, 4 -> 215, 3 -> 222, 2 -> 247
+    double h = sqrt(omega*per_cell*(double)(nth ? nth : 1)/(double)(n_cand ? n_cand : 1))*180.0/pi;   // [deg]
     if (h < 1.0/3600.0) h = 1.0/3600.0;
     if (h > 10.0) h = 10.0;
     // rows: pad by one so that every source falls strictly inside
@@ -366,11 +408,10 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
         const double eps_lo = (2.0*wmax)*(2.0*wmax)/12.0 + 1e-14;
         ResRec* res = (ResRec*)result_records;
         const int rv = reverse ? 1 : 0;
-#define XM_FILT(S, W) sphere_nn_filter_kernel<S, W><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, \
-        d_out, refine_list, refine_count, rv, ctr)
-        if (self) { if (wrap) XM_FILT(true, true); else XM_FILT(true, false); }
-        else { if (wrap) XM_FILT(false, true); else XM_FILT(false, false); }
-#undef XM_FILT
+        if (self) sphere_nn_filter_kernel<true><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, d_out,
+                                                                         refine_list, refine_count, rv, ctr);
+        else sphere_nn_filter_kernel<false><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, d_out,
+                                                                       refine_list, refine_count, rv, ctr);
         XM_CUDA_TRY(cudaGetLastError());
         *launches += 1;
         rows = refine_list;
