@@ -17,6 +17,9 @@
 // reaches the current nth-best; rows touching a pole have min cos = 0 and are scanned whole, which
 // is what makes the result exact there. Every surviving candidate is evaluated with the
 // reference-order proxy (xm_math_exact.cuh) and inserted by (proxy, row) lexicographic order.
+//
+// nth = 1 on small cells runs sphere_nn_filter_kernel first (a cheap, rigorous decision from the
+// 3x3 block around the source) and the exact kernel only on the rows that kernel cannot decide.
 #include "xm_common.cuh"
 #include "xm_math_exact.cuh"
 #include "xm_filter_common.cuh"
@@ -183,14 +186,18 @@ sphere_search_kernel(SphereGrid sg, CatView src, CatView cand, int self_mode, ui
 
 // ---- nearest-neighbour filter (nth = 1) ------------------------------------------------------------------
 // Same contract as ring_nn_filter_kernel of the cell-binned path: rank the candidates of the 3x3 cell
-// block with the cheap metric Q = dy^2 + dx^2 cos cos (dx wrapped into [-pi, pi]), tracked by its high
-// word; accept the row only if (1) everything outside the block is provably farther than the winner and
-// (2) the winner beats the runner-up by more than the metric's uncertainty (4p in [Q(1 - M/12), Q],
-// M <= (2 max(w))^2 inside the block); then evaluate the reference-order proxy of the winning pair once.
-// Any other row is appended to the list the exact kernel above walks afterwards.
-// The body is kept small on purpose (one rolled loop over the nine cells, polynomial bounds, the
-// small-angle sine only): the first version unrolled everything, grew to 4700 SASS instructions and
-// spent 58 % of its issue slots waiting for instruction fetches.
+// block with the cheap metric Q = dy^2 + dx^2 cos cos, tracked by its high word; accept the row only
+// if (1) everything outside the block is provably farther than the winner and (2) the winner beats
+// the runner-up by more than the metric's uncertainty (4p in [Q(1 - M/12), Q], M <= (2 max(w))^2
+// inside the block); then evaluate the reference-order proxy of the winning pair once. Any other
+// row -- grid edge, polar rows, the two columns at the RA seam, exact duplicates, incomplete blocks --
+// is appended to the list the exact kernel above walks afterwards (1.4 % of the rows on a uniform
+// full sky: the polar caps, where the fixed-width RA columns are physically narrow).
+// What ncu said about the earlier forms (profiles/README.md): fully unrolled with the libm-grade sine
+// it was 4700 SASS instructions and spent 58 % of its issue slots waiting for instruction fetches;
+// rolled into one lockstep loop over the nine cells it kept 7.8 of 32 lanes busy and spent 29 % of
+// its instructions on the FP64 selects of the RA wrap. Hence the shape below: polynomial bounds and
+// the small-angle sine only, no wrap, and the three phases A / B / C.
 using filt::kInfHi; using filt::hi_floor; using filt::hi_ceil; using filt::ResRec; using filt::store_res;
 
 // cell order: own, N, S, E, W, NE, NW, SE, SW (sides before corners, so that the best shrinks early);

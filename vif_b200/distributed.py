@@ -7,9 +7,14 @@ of catalog-1 rows per worker (qxmatch.hpp:422-459) -- with one exchange step for
      every rank bins with the grid of qxmatch.hpp:232-267 computed from the WHOLE catalogs;
   3. every rank runs the single-GPU pipeline on its row shard against the full catalog 2
      (forward results never leave the rank: rows are independent);
-  4. reverse match: all-reduce(min) on `rd`, then all-reduce(min) on `rid` masked to the ranks
-     whose local distance equals the global minimum => nearest catalog-1 row over all shards, the
-     smallest row index on exact ties (the reference's thread=1 rule, qxmatch.hpp:510-513).
+  4. reverse match: nearest catalog-1 row over all shards, the smallest global row index on exact
+     ties (the reference's thread=1 rule, qxmatch.hpp:510-513). On GPUs this is ONE kernel over
+     NVLink peer memory (xm_rev_merge_p2p): every rank's search writes (rd, rid) straight into a
+     peer-mapped exchange buffer, each rank merges its 1/N slice of the rows out of its peers'
+     buffers and stores the merged rows into every peer; torch symmetric memory supplies the
+     mappings and the two device-side barriers. Fallback (no peer mappings, XM_MERGE=nccl, CPU
+     tensors): all-reduce(min) on `rd`, then all-reduce(min) on `rid` masked to the ranks whose
+     local distance equals the global minimum.
 
 No collective touches the forward path. `compute` and `bbox` are injectable so that the sharding
 and merge logic is testable on CPU with the gloo backend (tests/test_distributed_gloo.py); the
