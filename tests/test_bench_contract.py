@@ -1,0 +1,50 @@
+"""bench.py's reference arm runs on CPU (the compiled reference or the oracle port): check the JSON
+line it prints against the contract keys. The GPU arm's line is checked on the GPU box (test_gpu_bench)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config"}
+
+
+def _run(*args, env=None):
+    e = dict(os.environ, **(env or {}))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         timeout=600, env=e, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = [l for l in _run("--impl", "reference", "--steps", "1", "--warmup", "0").splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert KEYS <= set(d)
+    assert d["impl"] == "reference" and d["metric"] == "qxmatch_sources_per_sec" and d["unit"] == "sources/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "sample" in d["config"]
+
+
+def test_reference_arm_other_ranks_are_silent():
+    assert _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--gpus", "2",
+                env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_bench_line_has_roofline_and_e2e():
+    lines = [l for l in _run("--steps", "3", "--warmup", "3", "--rows", "1000000", "--no-cpu").splitlines()
+             if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert KEYS <= set(d)
+    assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and 0 < r["frac"] < 1 and r["unit"] == "GB/s"
+    assert d["clocks"] is not None and d["step_ms_rank0"]["min"] > 0
