@@ -210,7 +210,7 @@ constexpr uint32_t pack9(int a0, int a1, int a2, int a3, int a4, int a5, int a6,
 constexpr uint32_t kNbX = pack9(0, 0, 0, 1, -1, 1, -1, 1, -1);
 constexpr uint32_t kNbY = pack9(0, 1, -1, 0, 0, 1, 1, -1, -1);
 
-template <bool SELF>
+template <bool SELF, bool QUEUE>
 __global__ void __launch_bounds__(kThreads)
 sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo, ResRec* __restrict__ res,
                         uint64_t* __restrict__ id_out, double* __restrict__ d_out,
@@ -271,8 +271,72 @@ sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo,
                (fma(Qe, sn, Qn) < thr ? 32u : 0u) | (fma(Qw, sn, Qn) < thr ? 64u : 0u) |
                (fma(Qe, ss, Qs) < thr ? 128u : 0u) | (fma(Qw, ss, Qs) < thr ? 256u : 0u);
     }
-    // ---- C. one flat loop over the candidates of the surviving neighbours ------------------------------
-    // A lane moves on to its next cell on its own, so the warp runs for the longest lane's total, not
+    // ---- C. the surviving neighbours ---------------------------------------------------------------------
+    if (QUEUE) {
+        // Warp-level work queue: the (source, cell) pairs of the 32 sources -- 0.6 per source on
+        // average, but 0..8 per lane -- are enumerated with ballots (cell by cell, lane by lane) and
+        // dealt one per lane; the lane scans that cell for the owner's source (fetched with
+        // shuffles) and the owner collects the partial results with shuffles. The warp runs for the
+        // largest CELL, not for the lane with the most cells.
+        __shared__ uint16_t s_item[kThreads/32][256];      // pair j of the warp -> owner lane | cell << 5
+        uint16_t* items = s_item[threadIdx.x >> 5];
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned bal[9], base[9];
+        unsigned total = 0;
+#pragma unroll
+        for (int e = 1; e <= 8; ++e) {
+            bal[e] = __ballot_sync(0xffffffffu, (todo >> e) & 1u);
+            base[e] = total;
+            if ((todo >> e) & 1u) items[total + __popc(bal[e] & lt)] = (uint16_t)(lane | ((unsigned)e << 5));
+            total += __popc(bal[e]);
+        }
+        __syncwarp();
+        for (unsigned r0 = 0; r0 < total; r0 += 32u) {
+            const unsigned j = r0 + lane;
+            int my_e = 0;
+            unsigned owner = lane;
+            if (j < total) { const unsigned it = items[j]; owner = it & 31u; my_e = (int)(it >> 5); }
+            const double ox1 = __shfl_sync(0xffffffffu, x1, owner), oy1 = __shfl_sync(0xffffffffu, y1, owner);
+            const double oc1 = __shfl_sync(0xffffffffu, c1, owner);
+            const uint32_t okey = __shfl_sync(0xffffffffu, me.key, owner);
+            const uint32_t oidx = __shfl_sync(0xffffffffu, me.idx, owner);
+            int32_t a1 = kInfHi, a2 = kInfHi;
+            uint32_t aslot = kNone, qq = 0, qqe = 0;
+            if (my_e) {
+                const int bx = (int)((kNbX >> (2*my_e)) & 3u) - 1, by = (int)((kNbY >> (2*my_e)) & 3u) - 1;
+                const uint32_t k = okey + (uint32_t)(bx*(int32_t)g.ndec + by);
+                qq = cand.cstart[k]; qqe = cand.cstart[k + 1];
+                evals += qqe - qq;
+            }
+            for (; qq < qqe; ++qq) {
+                const Rec cd = filt::load_rec(cand.rec + qq);
+                const double dx = cd.x - ox1, dy = cd.y - oy1;
+                int32_t h = __double2hiint(fma(dx*dx*cd.c, oc1, dy*dy));
+                if (SELF && cd.idx == oidx) h = kInfHi;
+                const bool better = h < a1;
+                a2 = min(a2, max(a1, h));
+                a1 = min(a1, h);
+                aslot = better ? qq : aslot;
+            }
+#pragma unroll
+            for (int e = 1; e <= 8; ++e) {
+                const unsigned je = base[e] + __popc(bal[e] & lt);          // my pair for cell e, if I have one
+                const bool mine = ((todo >> e) & 1u) && je >= r0 && je < r0 + 32u;
+                const unsigned from = (je - r0) & 31u;
+                const int32_t b1 = __shfl_sync(0xffffffffu, a1, from), b2 = __shfl_sync(0xffffffffu, a2, from);
+                const uint32_t bs = __shfl_sync(0xffffffffu, aslot, from);
+                if (mine) {
+                    const bool better = b1 < h1;
+                    h2 = min(min(h2, b2), max(h1, b1));
+                    h1 = min(h1, b1);
+                    slot = better ? bs : slot;
+                }
+            }
+        }
+    } else {
+    // One flat loop over the candidates of the surviving neighbours:
+    // a lane moves on to its next cell on its own, so the warp runs for the longest lane's total, not
     // for the sum of the per-cell maxima (walking the nine cells in lockstep kept 7.8 of 32 lanes busy).
     // Every lane of the warp stays in the loop until the last one is done: the pop branch and the
     // evaluation reconverge each iteration.
@@ -297,6 +361,7 @@ sphere_nn_filter_kernel(SphereGrid sg, CatView src, CatView cand, double eps_lo,
             active = found;
         }
         if (active) XM_EVAL()
+    }
     }
 #undef XM_EVAL
 
@@ -415,10 +480,14 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
         const double eps_lo = (2.0*wmax)*(2.0*wmax)/12.0 + 1e-14;
         ResRec* res = (ResRec*)result_records;
         const int rv = reverse ? 1 : 0;
-        if (self) sphere_nn_filter_kernel<true><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, d_out,
-                                                                         refine_list, refine_count, rv, ctr);
-        else sphere_nn_filter_kernel<false><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, d_out,
-                                                                       refine_list, refine_count, rv, ctr);
+        // warp-level queue for the neighbour cells (C5 on one B200: 204 -> 174 ms); XM_SPHERE_QUEUE=0
+        // selects the per-lane flat loop instead (kept for A/B runs)
+        static const bool queue = [] { const char* e = getenv("XM_SPHERE_QUEUE"); return !(e && e[0] == '0'); }();
+#define XM_FILT(S, Q) sphere_nn_filter_kernel<S, Q><<<full, kThreads, 0, s>>>(sg, src, cand, eps_lo, res, id_out, \
+        d_out, refine_list, refine_count, rv, ctr)
+        if (self) { if (queue) XM_FILT(true, true); else XM_FILT(true, false); }
+        else { if (queue) XM_FILT(false, true); else XM_FILT(false, false); }
+#undef XM_FILT
         XM_CUDA_TRY(cudaGetLastError());
         *launches += 1;
         rows = refine_list;
