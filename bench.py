@@ -427,7 +427,7 @@ def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_ac
             "gpu_launches": int(launches.item()),
             "step_ms_rank0": args.step_ms,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": ("sphere_search_kernel (forward + reverse launches)" if args.config == "c5" else
+            "roofline": {"bound": "hbm", "kernel": ("sphere_nn_filter_kernel + list-mode sphere_search_kernel (forward and reverse lanes, concurrent)" if args.config == "c5" else
                                                    "ring_nn_filter_kernel (forward + reverse launches, run concurrently)"), "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic, "peak_source": how,
