@@ -203,6 +203,25 @@ int32_t xm_rev_merge_p2p(const void* const* exch, void* const* out, uint64_t n, 
                          double unmatched, int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
 /*
+ * Distance helpers of the same haversine family, device pointers on `device`:
+ *   xm_angdist_dev       astro/astro.hpp:33-81: out[i] = angdist(ra1[i],dec1[i], ra2[k],dec2[k]) in arcsec,
+ *                        k = i, or 0 when second_is_scalar (the (vec, vec, double, double) overload);
+ *   xm_angdist_less_dev  astro/astro.hpp:83-103: out[i] = 1 where the point lies within `radius` arcsec
+ *                        of (ra2, dec2) -- the proxy comparison, no asin;
+ *   xm_qdist_dev         astro/qxmatch.hpp:684-717: n x n row-major matrix, out[j*n+i] = distance of
+ *                        rows i and j in arcsec for j > i, 0 elsewhere.
+ * Degrees in. Synchronous.
+ */
+int32_t xm_angdist_dev(const double* ra1, const double* dec1, const double* ra2, const double* dec2, uint64_t n,
+                       int32_t second_is_scalar, double* out, int32_t device, void* stream, char* errbuf,
+                       uint64_t errcap);
+int32_t xm_angdist_less_dev(const double* ra1, const double* dec1, uint64_t n, double ra2, double dec2,
+                            double radius, uint8_t* out, int32_t device, void* stream, char* errbuf,
+                            uint64_t errcap);
+int32_t xm_qdist_dev(const double* ra, const double* dec, uint64_t n, double* out, int32_t device, void* stream,
+                     char* errbuf, uint64_t errcap);
+
+/*
  * Mutual-best filter on the device (replaces xmatch_clean_best, qxmatch.hpp:641-663, while id/rid
  * are still resident): row i of catalog 1 is kept when rid[id[i]] == i. id = rank-0 plane (n1), rid
  * (n2). Outputs (caller-allocated, n1 elements each): id1/id2 = the kept pairs in ascending i, lost =

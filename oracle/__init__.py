@@ -5,4 +5,6 @@ Nothing under vif_b200/ does (checked by tests/test_no_oracle_in_product.py).
 """
 from .oracle import (OracleGrid, have_ref, oracle_qxmatch, oracle_grid, oracle_ring,  # noqa: F401
                      oracle_field_area_bbox, oracle_angdist, ref_qxmatch, ref_ring,
-                     ref_field_area_bbox, ref_angdist, build, NPOS)
+                     ref_field_area_bbox, ref_angdist, build, NPOS,
+                     oracle_angdist_vec, oracle_angdist_less, oracle_qdist,
+                     ref_angdist_vec, ref_angdist_less, ref_qdist)

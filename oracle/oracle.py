@@ -64,6 +64,7 @@ def _load_port():
         lib.oracle_field_area_bbox.argtypes = [C.c_double] * 4
         lib.oracle_angdist.restype = C.c_double
         lib.oracle_angdist.argtypes = [C.c_double] * 4
+        _bind_dist(lib, "oracle")
         _port = lib
     return _port
 
@@ -84,6 +85,7 @@ def _load_ref():
         lib.ref_field_area_bbox.argtypes = [C.c_double] * 4
         lib.ref_angdist.restype = C.c_double
         lib.ref_angdist.argtypes = [C.c_double] * 4
+        _bind_dist(lib, "ref")
         lib.ref_ring.restype = _u64
         lib.ref_ring.argtypes = [_u64, _u64, C.c_double, _u64, _ip, _ip, _u64, _dp]
         lib.ref_hardware_threads.restype = _u64
@@ -168,6 +170,73 @@ def oracle_field_area_bbox(r0, r1, d0, d1):
 
 def ref_field_area_bbox(r0, r1, d0, d1):
     return _load_ref().ref_field_area_bbox(r0, r1, d0, d1)
+
+
+def _bind_dist(lib, prefix):
+    f = getattr(lib, prefix + "_angdist_vec")
+    f.restype = None
+    f.argtypes = [_dp, _dp, _u64, _dp, _dp, _u64, _dp]
+    f = getattr(lib, prefix + "_angdist_less")
+    f.restype = None
+    f.argtypes = [_dp, _dp, _u64, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_uint8)]
+    f = getattr(lib, prefix + "_qdist")
+    f.restype = None
+    f.argtypes = [_dp, _dp, _u64, _dp]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+
+
+def _dist_calls(lib, prefix):
+    def angdist_vec(ra1, dec1, ra2, dec2):
+        a1, b1, a2, b2 = _f64(ra1), _f64(dec1), _f64(ra2), _f64(dec2)
+        out = np.empty(a1.size)
+        getattr(lib, prefix + "_angdist_vec")(a1.ctypes.data_as(_dp), b1.ctypes.data_as(_dp), a1.size,
+                                              a2.ctypes.data_as(_dp), b2.ctypes.data_as(_dp), a2.size,
+                                              out.ctypes.data_as(_dp))
+        return out
+
+    def angdist_less(ra1, dec1, ra2, dec2, radius):
+        a1, b1 = _f64(ra1), _f64(dec1)
+        out = np.empty(a1.size, dtype=np.uint8)
+        getattr(lib, prefix + "_angdist_less")(a1.ctypes.data_as(_dp), b1.ctypes.data_as(_dp), a1.size, float(ra2),
+                                               float(dec2), float(radius), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.astype(bool)
+
+    def qdist(ra, dec):
+        a, b = _f64(ra), _f64(dec)
+        out = np.empty((a.size, a.size))
+        getattr(lib, prefix + "_qdist")(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), a.size, out.ctypes.data_as(_dp))
+        return out
+    return angdist_vec, angdist_less, qdist
+
+
+def oracle_angdist_vec(ra1, dec1, ra2, dec2):
+    """astro.hpp:43-81 (ra2/dec2 of one element = the scalar overload)."""
+    return _dist_calls(_load_port(), "oracle")[0](ra1, dec1, ra2, dec2)
+
+
+def oracle_angdist_less(ra1, dec1, ra2, dec2, radius):
+    """astro.hpp:83-103."""
+    return _dist_calls(_load_port(), "oracle")[1](ra1, dec1, ra2, dec2, radius)
+
+
+def oracle_qdist(ra, dec):
+    """qxmatch.hpp:684-717."""
+    return _dist_calls(_load_port(), "oracle")[2](ra, dec)
+
+
+def ref_angdist_vec(ra1, dec1, ra2, dec2):
+    return _dist_calls(_load_ref(), "ref")[0](ra1, dec1, ra2, dec2)
+
+
+def ref_angdist_less(ra1, dec1, ra2, dec2, radius):
+    return _dist_calls(_load_ref(), "ref")[1](ra1, dec1, ra2, dec2, radius)
+
+
+def ref_qdist(ra, dec):
+    return _dist_calls(_load_ref(), "ref")[2](ra, dec)
 
 
 def oracle_angdist(a, b, c, d):

@@ -69,6 +69,48 @@ double oracle_angdist(double tra1, double tdec1, double tra2, double tdec2) {
     return 3600.0*2.0*asin(sqrt(sde*sde + sra*sra*cos(dec2)*cos(dec1)))/d2r;
 }
 
+/* vector forms: astro.hpp:43-81 (element-wise; ra2/dec2 scalar when n2 == 1) */
+void oracle_angdist_vec(const double* ra1, const double* dec1, uint64_t n, const double* ra2,
+                        const double* dec2, uint64_t n2, double* out) {
+    for (uint64_t i = 0; i < n; ++i)
+        out[i] = oracle_angdist(ra1[i], dec1[i], ra2[n2 == 1 ? 0 : i], dec2[n2 == 1 ? 0 : i]);
+}
+
+/* angdist_less, astro.hpp:83-103: proxy < sqr(sin(rrad/2)), no asin */
+void oracle_angdist_less(const double* tra1, const double* tdec1, uint64_t n, double tra2, double tdec2,
+                         double radius, uint8_t* out) {
+    const double d2r = DPI/180.0;
+    const double rrad = d2r*radius/3600.0;
+    const double sr = sin(rrad/2.0);
+    const double crad = sr*sr;
+    for (uint64_t i = 0; i < n; ++i) {
+        double ra1 = d2r*tra1[i], ra2 = d2r*tra2;
+        double dec1 = d2r*tdec1[i], dec2 = d2r*tdec2;
+        double sra = sin(0.5*(ra2 - ra1));
+        double sde = sin(0.5*(dec2 - dec1));
+        out[i] = (sde*sde + sra*sra*cos(dec2)*cos(dec1) < crad) ? 1 : 0;
+    }
+}
+
+/* qdist, qxmatch.hpp:684-717: n x n matrix, ret(j,i) for j > i, everything else 0 */
+void oracle_qdist(const double* ra, const double* dec, uint64_t n, double* out) {
+    const double d2r = DPI/180.0;
+    double* dra = (double*)malloc(3*n*sizeof(double) + 8);
+    double* ddec = dra + n;
+    double* dcdec = ddec + n;
+    for (uint64_t i = 0; i < n; ++i) { dra[i] = ra[i]*d2r; ddec[i] = dec[i]*d2r; dcdec[i] = cos(ddec[i]); }
+    memset(out, 0, n*n*sizeof(double));
+    for (uint64_t i = 0; i < n; ++i) {
+        for (uint64_t j = i + 1; j < n; ++j) {
+            double sra = sin(0.5*(dra[j] - dra[i]));
+            double sde = sin(0.5*(ddec[j] - ddec[i]));
+            double d = sde*sde + sra*sra*dcdec[j]*dcdec[i];
+            out[j*n + i] = 3600.0*(180.0/DPI)*2*asin(sqrt(d));
+        }
+    }
+    free(dra);
+}
+
 /* ---- hull of <= 4 points + spherical Heron area (convex_hull.hpp:108-150, astro.hpp:524-552) */
 static double cross3(const double* x, const double* y, int i, int j, int k) {
     return (x[j] - x[i])*(y[k] - y[i]) - (y[j] - y[i])*(x[k] - x[i]);

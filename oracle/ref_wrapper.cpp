@@ -60,6 +60,36 @@ double ref_angdist(double ra1, double dec1, double ra2, double dec2) {
     return angdist(ra1, dec1, ra2, dec2);
 }
 
+// vector angdist (astro.hpp:43-81), angdist_less (astro.hpp:83-103), qdist (qxmatch.hpp:684-717)
+void ref_angdist_vec(const double* ra1, const double* dec1, uint64_t n, const double* ra2,
+                     const double* dec2, uint64_t n2, double* out) {
+    vec1d a1(n), b1(n);
+    for (uint64_t i = 0; i < n; ++i) { a1[i] = ra1[i]; b1[i] = dec1[i]; }
+    vec1d r;
+    if (n2 == 1) r = angdist(a1, b1, ra2[0], dec2[0]);
+    else {
+        vec1d a2(n), b2(n);
+        for (uint64_t i = 0; i < n; ++i) { a2[i] = ra2[i]; b2[i] = dec2[i]; }
+        r = angdist(a1, b1, a2, b2);
+    }
+    for (uint64_t i = 0; i < n; ++i) out[i] = r[i];
+}
+
+void ref_angdist_less(const double* ra1, const double* dec1, uint64_t n, double ra2, double dec2,
+                      double radius, uint8_t* out) {
+    vec1d a1(n), b1(n);
+    for (uint64_t i = 0; i < n; ++i) { a1[i] = ra1[i]; b1[i] = dec1[i]; }
+    vec1b r = angdist_less(a1, b1, ra2, dec2, radius);
+    for (uint64_t i = 0; i < n; ++i) out[i] = r[i] ? 1 : 0;
+}
+
+void ref_qdist(const double* ra, const double* dec, uint64_t n, double* out) {
+    vec1d a(n), b(n);
+    for (uint64_t i = 0; i < n; ++i) { a[i] = ra[i]; b[i] = dec[i]; }
+    vec2d r = qdist(a, b);
+    for (uint64_t k = 0; k < n*n; ++k) out[k] = r.data[k];
+}
+
 // Ring table dump (depth_cache, qxmatch.hpp:44-128). Writes ring `k` of a grid
 // (nx, ny, cs) into bx/by (capacity cap); returns the entry count, max_dist in *md.
 uint64_t ref_ring(uint64_t nx, uint64_t ny, double cs, uint64_t k,

@@ -42,7 +42,7 @@ class XmStats(C.Structure):
 
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
-SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_qxmatch_f64", "xm_qxmatch_dev",
+SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
            "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
@@ -91,6 +91,12 @@ def load():
     lib.xm_rev_merge_mask.argtypes = [vp, vp, vp, u64, i32, vp, C.c_char_p, u64]
     lib.xm_rev_merge_unpack.restype = i32
     lib.xm_rev_merge_unpack.argtypes = [vp, vp, vp, u64, f64, i32, vp, C.c_char_p, u64]
+    lib.xm_angdist_dev.restype = i32
+    lib.xm_angdist_dev.argtypes = [vp, vp, vp, vp, u64, i32, vp, i32, vp, C.c_char_p, u64]
+    lib.xm_angdist_less_dev.restype = i32
+    lib.xm_angdist_less_dev.argtypes = [vp, vp, u64, f64, f64, f64, vp, i32, vp, C.c_char_p, u64]
+    lib.xm_qdist_dev.restype = i32
+    lib.xm_qdist_dev.argtypes = [vp, vp, u64, vp, i32, vp, C.c_char_p, u64]
     lib.xm_rev_merge_p2p.restype = i32
     lib.xm_rev_merge_p2p.argtypes = [C.POINTER(vp), C.POINTER(vp), u64, i32, i32, f64, i32, vp, C.c_char_p, u64]
     _lib = lib

@@ -664,6 +664,30 @@ int32_t check_args(const double* ra1, const double* dec1, uint64_t n1, const dou
     return XM_OK;
 }
 
+// shared shape of the small distance entry points (xm_dist.cu)
+template <class F>
+int32_t dist_entry(int32_t device, void* stream, char* errbuf, uint64_t errcap, bool bad_args, F&& f) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = bad_args ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            int32_t r = f(ctx, s, err);
+            if (r) return r;
+            XM_CUDA_TRY(cudaStreamSynchronize(s));
+            return XM_OK;
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
 }  // namespace
 }  // namespace xm
 
@@ -945,6 +969,34 @@ int32_t xm_rev_merge_p2p(const void* const* exch, void* const* out, uint64_t n, 
     }
     if (rc) copy_err(err, errbuf, errcap);
     return rc;
+}
+
+int32_t xm_angdist_dev(const double* ra1, const double* dec1, const double* ra2, const double* dec2, uint64_t n,
+                       int32_t second_is_scalar, double* out, int32_t device, void* stream, char* errbuf,
+                       uint64_t errcap) {
+    return dist_entry(device, stream, errbuf, errcap, n && (!ra1 || !dec1 || !ra2 || !dec2 || !out),
+                      [&](Context* ctx, cudaStream_t s, Error& err) {
+                          return launch_angdist(ra1, dec1, ra2, dec2, n, second_is_scalar != 0, ctx->sin_model, out, s, err);
+                      });
+}
+
+int32_t xm_angdist_less_dev(const double* ra1, const double* dec1, uint64_t n, double ra2, double dec2,
+                            double radius, uint8_t* out, int32_t device, void* stream, char* errbuf,
+                            uint64_t errcap) {
+    return dist_entry(device, stream, errbuf, errcap, n && (!ra1 || !dec1 || !out),
+                      [&](Context* ctx, cudaStream_t s, Error& err) {
+                          return launch_angdist_less(ra1, dec1, n, ra2, dec2, radius, ctx->sin_model, out, s, err);
+                      });
+}
+
+int32_t xm_qdist_dev(const double* ra, const double* dec, uint64_t n, double* out, int32_t device, void* stream,
+                     char* errbuf, uint64_t errcap) {
+    return dist_entry(device, stream, errbuf, errcap, n && (!ra || !dec || !out),
+                      [&](Context* ctx, cudaStream_t s, Error& err) -> int32_t {
+                          Scratch scr;
+                          XM_CUDA_TRY(scr.alloc(qdist_scratch_bytes(n), s));
+                          return launch_qdist(ra, dec, n, ctx->sin_model, scr.p, out, s, err);
+                      });
 }
 
 int32_t xm_clean_best_dev(const uint64_t* id, const uint64_t* rid, uint64_t n1, uint64_t n2, uint64_t* id1,

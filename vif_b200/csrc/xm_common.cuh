@@ -80,6 +80,15 @@ int  calibrate_sin_model();   // probes the host libm: 1 = FMA Taylor model, 2 =
 // xm_index.cu
 int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned long long* out5,
                     cudaStream_t s, Error& err, uint64_t* launches);
+// distance helpers (xm_dist.cu)
+int32_t launch_angdist(const double* ra1, const double* dec1, const double* ra2, const double* dec2, uint64_t n,
+                       bool scalar2, int model, double* out, cudaStream_t s, Error& err);
+int32_t launch_angdist_less(const double* ra1, const double* dec1, uint64_t n, double tra2, double tdec2,
+                            double radius, int model, uint8_t* out, cudaStream_t s, Error& err);
+size_t  qdist_scratch_bytes(uint64_t n);
+int32_t launch_qdist(const double* ra, const double* dec, uint64_t n, int model, void* scratch, double* out,
+                     cudaStream_t s, Error& err);
+
 // pageable host buffers (xm_staging.cu)
 struct StageJob { void* dev; void* host; size_t bytes; };
 bool    host_pointer_is_pageable(const void* p);
