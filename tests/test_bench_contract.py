@@ -37,6 +37,16 @@ def test_reference_arm_other_ranks_are_silent():
                 env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
 
 
+def test_cpu_baseline_leg():
+    sys.path.insert(0, ROOT)
+    import bench
+    b = bench.measure_cpu_baseline(budget_s=1.0)
+    assert b["unit"] == "sources/s" and b["kind"] in ("reference", "port") and b["cores"] >= 1
+    assert b["value"] > 0 and json.dumps(b)
+    if b["cores"] > 1:
+        assert 0 < b["value_1_thread"] < 1.5*b["value"]
+
+
 @pytest.mark.gpu
 def test_gpu_bench_line_has_roofline_and_e2e():
     lines = [l for l in _run("--steps", "3", "--warmup", "3", "--rows", "1000000", "--no-cpu").splitlines()
