@@ -191,6 +191,7 @@ def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, 
 
 
 _P2P = {}           # (device, n, world, group) -> symmetric buffers of the peer-memory merge
+_P2P_MAX = 4        # distinct catalog-2 sizes that get peer-mapped buffers (32 n + 8 bytes each per rank)
 _P2P_OFF = set()    # groups on which symmetric memory could not be set up: NCCL merge from then on
 
 
@@ -243,6 +244,8 @@ def _p2p_buffers(n, dev, world, group):
         return None
     key = (dev.index or 0, n, world, gkey)
     ent = _P2P.get(key)
+    if ent is None and len(_P2P) >= _P2P_MAX:
+        return None          # the buffers are per catalog-2 size and never freed: further sizes merge through NCCL
     if ent is None:
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
