@@ -15,7 +15,6 @@ One "step" = one complete qxmatch of the workload. Prints ONE JSON line on rank 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

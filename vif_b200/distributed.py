@@ -23,8 +23,6 @@ defaults are the CUDA library and there is no CPU implementation in this module.
 import os
 import time
 
-import numpy as np
-
 
 def shard_bounds(n, world_size, rank):
     """Contiguous row block [begin, end) of `rank` (floor split, remainder to the last ranks)."""
