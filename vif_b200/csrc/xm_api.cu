@@ -472,6 +472,10 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         // every tie, the K=1 exact kernel breaks in-cell ties by row), so the bucket index may
         // leave cells in arrival order.
         const bool unordered = use_bucket && fast && nth_eff == 1;
+        // XM_FILTER=v1 keeps the FP64 filter kernel (xm_search_fast.cu) for every call; by default it only
+        // serves the catalogs whose density does not suit the FP32 kernel's stage (xm_search_nn32.cu)
+        const char* fenv = getenv("XM_FILTER");
+        const bool filter_v1 = fenv && strcmp(fenv, "v1") == 0;
         // Two lanes: `s` indexes catalog 1 and runs the forward search, `s2` indexes catalog 2 and
         // runs the reverse search. The lanes only meet where one needs the other's index.
         cudaStream_t s2 = ctx->stream2;
@@ -516,11 +520,19 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         } else if (fast && nth_eff == 1) {
             XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
             XM_CUDA_TRY(resrec.alloc(filter_result_bytes(n1o), s));
-            XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
             // filter -> (unpack on s || exact kernel of the undecided rows on a side stream) -> join
-            if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
-                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
-                                            &launches))) return rc;
+            const int tile = filter_v1 ? 0 : nn32_tile_sources(g, srcF->n, v2->n);
+            if (tile) {
+                XM_CUDA_TRY(plans.alloc(nn32_plan_bytes(n1o, g.nra, tile), s));
+                if ((rc = launch_ring_nn32(g, *srcF, *v2, self, tile, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
+                                           &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
+                                           &launches))) return rc;
+            } else {
+                XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
+                if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
+                                                &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
+                                                &launches))) return rc;
+            }
             XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[0], ctx->lane_ev[0], 0));
             if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
                                                (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr,
@@ -554,10 +566,18 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                 if (fast) {
                     XM_CUDA_TRY(refine2.alloc((size_t)n2o*4, s2));
                     XM_CUDA_TRY(resrec2.alloc(filter_result_bytes(n2o), s2));
-                    XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
-                    if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,
-                                                    refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
-                                                    s2, ctx->lane_ev[2], err, &launches))) return rc;
+                    const int tile = filter_v1 ? 0 : nn32_tile_sources(g, srcR->n, s1.view.n);
+                    if (tile) {
+                        XM_CUDA_TRY(plans2.alloc(nn32_plan_bytes(n2o, g.nra, tile), s2));
+                        if ((rc = launch_ring_nn32(g, *srcR, s1.view, false, tile, rid, rd, resrec2.p, plans2.p,
+                                                   refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
+                                                   s2, ctx->lane_ev[2], err, &launches))) return rc;
+                    } else {
+                        XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
+                        if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,
+                                                        refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
+                                                        s2, ctx->lane_ev[2], err, &launches))) return rc;
+                    }
                     XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[1], ctx->lane_ev[2], 0));
                     if ((rc = launch_ring_search_exact(g, *srcR, s1.view, 0, 1u, n2o, rid, rd,
                                                        refine2.as<uint32_t>(), (uint32_t)n2o,

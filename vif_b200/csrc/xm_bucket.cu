@@ -227,6 +227,11 @@ int32_t launch_clean_best(const uint64_t* id, const uint64_t* rid, uint32_t n1, 
     return XM_OK;
 }
 
+// in-place exclusive scan of data[0..n) for other translation units (aux: bucket_scan_aux_bytes(n))
+void launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches) {
+    exclusive_scan(data, n, aux, s, launches);
+}
+
 size_t bucket_scan_aux_bytes(uint32_t ncell) {
     uint64_t n = (uint64_t)ncell + 1, tot = 4;
     while (n > 1) { n = (n + kScanTile - 1)/kScanTile; tot += n + 1; }

@@ -109,6 +109,7 @@ int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, con
                                 uint64_t* launches);
 // xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
 size_t  bucket_scan_aux_bytes(uint32_t ncell);
+void    launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches);
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
                             uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
                             uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
@@ -140,6 +141,15 @@ size_t  filter_result_bytes(uint64_t n);     // scratch for the filter's sector-
 int32_t launch_unpack_results(const void* res, uint32_t n, uint64_t* id_out, double* d_out, cudaStream_t s,
                               Error& err, uint64_t* launches);
 size_t  filter_plan_bytes(uint64_t n);       // scratch for the per-tile staging plans
+// xm_search_nn32.cu: the same filter with an FP32 metric in a per-tile frame (catalogs of ordinary
+// density: a tile's 3-column neighbourhood must fit the shared-memory stage)
+int     nn32_tile_sources(const GridView& g, uint64_t n_src, uint64_t n_cand);   // 0: not applicable
+size_t  nn32_plan_bytes(uint64_t n_src, uint32_t nra, int tile);
+int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& cand, bool self, int tile,
+                         uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
+                         uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
+                         SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
+                         uint64_t* launches);
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,

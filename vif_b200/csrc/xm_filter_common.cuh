@@ -50,8 +50,9 @@ __device__ __forceinline__ double hi_ceil(int32_t h) {
 
 // Stop rule of qxmatch.hpp:336-340 on the small-angle forms. 0: stop for certain, 1: continue for
 // certain, 2: inside the slack. q1 is only known to lie in [q1_lo, q1_hi).
-__device__ __forceinline__ int stop_decision(double q1_lo, double q1_hi, double tr, const GridView& g) {
-    const double lo = tr - g.stop_delta, hi = tr + g.stop_delta;
+__device__ __forceinline__ int stop_decision(double q1_lo, double q1_hi, double tr, const GridView& g,
+                                             double extra_delta = 0.0) {
+    const double lo = tr - (g.stop_delta + extra_delta), hi = tr + (g.stop_delta + extra_delta);
     if (lo > 0.0 && q1_hi*(1.0 + g.eps_hi) <= lo*lo*(1.0 - lo*lo*(1.0/12.0) - 1e-12)) return 0;
     if (hi <= 0.0) return q1_lo > 0.0 ? 1 : 2;
     if (q1_lo*(1.0 - g.eps_lo) > hi*hi) return 1;
