@@ -256,6 +256,130 @@ ring_search_exact_kernel(GridView g, CatView src, CatView cand, int self_mode, u
     warp_add(&ctr->ambiguous, amb);
 }
 
+// ---- list mode, nth = 1: one WARP per flagged row ------------------------------------------------
+// The filter kernels hand over a few thousand rows per call. One thread per row (kernel above) is a
+// serial chain of ~60 dependent global loads per row (cell offsets, then candidates): ~130 us whatever
+// the list length. Here a warp owns a row: lane l resolves ring-1 entry l (range + lower bound) in
+// parallel, surviving cells are visited in the reference's order and each cell's candidates are
+// evaluated 32 at a time. Semantics are those of ring_search_row with a one-slot list:
+// strictly smaller proxies replace the best, so among equal proxies the first visited cell wins and,
+// inside a cell, the first row (ascending slot when cells are ordered, ascending original row when
+// they are not). Rows that must go beyond ring 1 fall back to ring_search_row on lane 0.
+struct WarpBest {
+    double   sd;       // best proxy
+    uint32_t q;        // its slot
+    double   second;   // smallest other proxy seen (ambiguity diagnostic, = RegList::rej)
+};
+
+template <bool UNORD>
+__device__ __forceinline__ void warp_scan_cell(const GridView& g, const CatView& cand, const Rec& me, int self_mode,
+                                               uint32_t p, uint32_t qs, uint32_t qe, WarpBest& B,
+                                               unsigned long long& evals) {
+    const int lane = threadIdx.x & 31;
+    double m1 = dinf(), m2 = dinf();
+    uint32_t mq = kNoCand, mord = 0xffffffffu;
+    for (uint32_t q = qs + lane; q < qe; q += 32) {
+        if (self_mode == 1 && q == p) continue;
+        const Rec cd = cand.rec[q];
+        if (self_mode == 2 && cd.idx == me.idx + g.self_off) continue;
+        const double sd = proxy_sph(me.x, me.y, me.c, cd.x, cd.y, cd.c, g.sin_model);
+        ++evals;
+        const uint32_t ord = UNORD ? cd.idx : q;
+        if (sd < m1 || (sd == m1 && ord < mord)) { m2 = m1; m1 = sd; mq = q; mord = ord; }
+        else m2 = fmin(m2, sd);
+    }
+    // lexicographic (proxy, order) minimum over the warp + the second smallest proxy
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a1 = __shfl_xor_sync(0xffffffffu, m1, o), a2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const uint32_t aq = __shfl_xor_sync(0xffffffffu, mq, o), ao = __shfl_xor_sync(0xffffffffu, mord, o);
+        const bool take = a1 < m1 || (a1 == m1 && ao < mord);
+        const double lose = take ? m1 : a1;
+        m2 = fmin(fmin(m2, a2), lose);
+        if (take) { m1 = a1; mq = aq; mord = ao; }
+    }
+    if (mq == kNoCand) return;
+    if (m1 < B.sd) { B.second = fmin(fmin(B.second, B.sd), m2); B.sd = m1; B.q = mq; }
+    else B.second = fmin(B.second, m1);          // m2 >= m1: m1 is the smallest rejected value of this cell
+}
+
+template <bool UNORD>
+__global__ void __launch_bounds__(kRingThreads)
+ring_list_nn_kernel(GridView g, CatView src, CatView cand, int self_mode, uint64_t* __restrict__ id_out,
+                    double* __restrict__ d_out, const uint32_t* __restrict__ rows, uint32_t nrows,
+                    const unsigned long long* __restrict__ nrows_dev, int reverse, SearchCounters* ctr) {
+    if (nrows_dev) { const unsigned long long c = *nrows_dev; nrows = c < nrows ? (uint32_t)c : nrows; }
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x*blockDim.x) >> 5;
+    unsigned long long evals = 0, amb = 0;
+    // ring-1 entry of this lane in the reference's order (axis cells once: a repeated visit cannot change a
+    // nearest-neighbour search with strict '<')
+    int mybx = 0, myby = 0, nent = 0;
+    if (g.max_depth > 1)
+        for_each_ring_entry(1, g.nra, g.ndec, true, [&](int bx, int by) { if (nent == lane) { mybx = bx; myby = by; } ++nent; });
+
+    for (uint32_t t = warp; t < nrows; t += nwarps) {
+        const uint32_t p = rows[t];
+        const Rec me = src.rec[p];
+        const int64_t x0 = me.key/g.ndec, y0 = me.key - (uint32_t)x0*g.ndec;
+        const double ccx = __dadd_rn(g.rra0,  __dmul_rn(__dadd_rn((double)x0, 0.5), g.dra));
+        const double ccy = __dadd_rn(g.rdec0, __dmul_rn(__dadd_rn((double)y0, 0.5), g.ddec));
+        const double cell_dist = angdist_pre(me.x, me.y, me.c, ccx, ccy, g.sin_model);
+        WarpBest B;
+        B.sd = dinf(); B.q = kNoCand; B.second = dinf();
+        // ring 0
+        warp_scan_cell<UNORD>(g, cand, me, self_mode, p, cand.cstart[me.key], cand.cstart[me.key + 1], B, evals);
+        auto reached_after = [&](uint32_t d) {
+            const double max_dist = d == 0 ? __ddiv_rn(g.cell_size, 2.0) : __dmul_rn(g.cell_size, __dadd_rn((double)(d + 1), 0.5));
+            const double tt = __dsub_rn(__dsub_rn(max_dist, __dmul_rn(1.1, cell_dist)), __dmul_rn(0.1, g.cell_size));
+            return true_to_proxy(tt > 0.0 ? tt : 0.0, false, g.sin_model);
+        };
+        bool deeper = false;
+        if (B.sd > reached_after(0) && 1 < g.max_depth) {
+            // ring 1: every lane resolves its entry, then the surviving cells are visited in order
+            uint32_t qs = 0, qe = 0;
+            double lb = dinf();
+            if (lane < nent) {
+                const int64_t cx = x0 + mybx, cy = y0 + myby;
+                if (cx >= 0 && cx < (int64_t)g.nra && cy >= 0 && cy < (int64_t)g.ndec) {
+                    const uint64_t ck = (uint64_t)cx*g.ndec + (uint64_t)cy;
+                    qs = cand.cstart[ck]; qe = cand.cstart[ck + 1];
+                    if (qs < qe) lb = cell_lower_bound<false>(g, me.x, me.y, me.c, cx, cy);
+                }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, qs < qe);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const double clb = __shfl_sync(0xffffffffu, lb, l);
+                const uint32_t cqs = __shfl_sync(0xffffffffu, qs, l), cqe = __shfl_sync(0xffffffffu, qe, l);
+                if (clb >= B.sd) continue;                          // culled exactly as in ring_search_row
+                warp_scan_cell<UNORD>(g, cand, me, self_mode, p, cqs, cqe, B, evals);
+            }
+            deeper = B.sd > reached_after(1) && 2 < g.max_depth;
+        }
+        if (deeper) {
+            // beyond ring 1 (sparse neighbourhoods): the general walk, from scratch, on one lane
+            if (lane == 0) {
+                RegList<1> L;
+                L.init();
+                unsigned long long ev = 0;
+                ring_search_row<RegList<1>, false, UNORD>(g, src, cand, self_mode, p, L, ev);
+                evals += ev;
+                B.sd = L.d[0]; B.q = L.q[0]; B.second = L.rej;
+            }
+        }
+        if (lane == 0) {
+            id_out[me.idx] = B.q == kNoCand ? XM_NPOS : (uint64_t)cand.rec[B.q].idx;
+            d_out[me.idx] = proxy_to_true(B.sd, false);
+            amb += near_tie(B.sd, B.second) ? 1 : 0;
+        }
+    }
+    __syncwarp();
+    warp_add(reverse ? &ctr->evals_rev : &ctr->evals_fwd, evals);
+    warp_add(&ctr->ambiguous, amb);
+}
+
 // ---- brute force -------------------------------------------------------------------------------
 template <int K, bool LINEAR>
 __global__ void __launch_bounds__(kBruteThreads)
@@ -395,6 +519,18 @@ int32_t launch_ring_search_exact(const GridView& g, const CatView& src, const Ca
                                  Error& err, uint64_t* launches) {
     if (nrows == 0 || nth_eff == 0) return XM_OK;
     const int unordered = (cells_unordered && nth_eff == 1) ? 1 : 0;
+    if (rows && nth_eff == 1 && !g.linear) {
+        // list of flagged rows of a nearest-neighbour search: one warp per row
+        const uint64_t want = ((uint64_t)nrows*32 + kRingThreads - 1)/kRingThreads;
+        const uint32_t nb = (uint32_t)(want < 148ull*16 ? want : 148ull*16);
+        if (unordered) ring_list_nn_kernel<true><<<nb, kRingThreads, 0, s>>>(g, src, cand, self, id_out, d_out, rows, nrows,
+                                                                              nrows_dev, reverse ? 1 : 0, ctr);
+        else ring_list_nn_kernel<false><<<nb, kRingThreads, 0, s>>>(g, src, cand, self, id_out, d_out, rows, nrows,
+                                                                    nrows_dev, reverse ? 1 : 0, ctr);
+        *launches += 1;
+        XM_CUDA_TRY(cudaGetLastError());
+        return XM_OK;
+    }
     uint32_t blocks = (nrows + kRingThreads - 1)/kRingThreads;
     if (nrows_dev && blocks > 148*4) blocks = 148*4;     // list of unknown (small) length: persistent grid
     const dim3 grid(blocks);
