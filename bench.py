@@ -9,8 +9,11 @@ One "step" = one complete qxmatch of the workload. Prints ONE JSON line on rank 
   value        whole-job sources/s with inputs resident in HBM (device pipeline only)
   e2e          the same through the host-buffer C-ABI call (xm_qxmatch_f64): H2D of the catalogs
                from pinned memory and D2H of id/d/rid/rd inside the timed region
-  roofline     the dominant kernel (ring search), algorithmic bytes / live CUDA-event time
-  cpu_baseline the reference (oracle/_ref) or its port timed on the host cores on a bounded sample
+  roofline     whole-path algorithmic bytes / step time against the measured HBM peak, with
+               the dominant kernel (nearest-neighbour filter, live CUDA-event time) beside it; --config c4:
+               11 flop/pair against the measured DFMA peak (profiles/fp64_peak.json)
+  cpu_baseline the reference (oracle/_ref) or its port timed on the host cores: the FULL workload once on
+               all threads (N = 1), a bounded sample on one thread
 """
 import argparse
 import json
@@ -27,10 +30,15 @@ import numpy as np  # noqa: E402
 METRIC = "qxmatch_sources_per_sec"
 UNIT = "sources/s"
 N_FULL = 10_000_000
-SAMPLE_N = 250_000          # CPU sample: sub-box with 1/40 of the area, same source density
+SAMPLE_N = 250_000          # one-thread CPU sample: sub-box with 1/40 of the area, same source density
+REF_ARM_N = 1_000_000       # reference arm, per step: sub-box with 1/10 of the area (a few seconds on 16 cores)
+C4_N = 1_000_000
 
 
 def workload_desc(n1, n2, config="c2"):
+    if config == "c4":
+        return ("C4: brute_force qxmatch %.0e x %.0e synthetic sources uniform on the full sky, nth=1, reverse match "
+                "(rid/rd) on" % (n1, n2))
     if config == "c3":
         return ("C3: self match (self=true) nth=5 on a %.0e-source clustered (Soneira-Peebles) synthetic catalog over "
                 "RA[0,10]xDec[-5,5], cell-binned" % n1)
@@ -49,7 +57,7 @@ def gen_catalog(G, config, seed, n, dev, start=0):
     step = 50_000_000
     for s0 in range(0, n, step):
         m = min(step, n - s0)
-        if config == "c5":
+        if config in ("c5", "c4"):
             a, b = G.fullsky(seed, m, xp="torch", device=dev, start=start + s0)
         else:
             a, b = G.c2(seed, m, xp="torch", device=dev, start=start + s0)
@@ -170,33 +178,52 @@ def cpu_runner(threads=None):
     return (lambda a1, b1, a2, b2: O.oracle_qxmatch(a1, b1, a2, b2, thread=cores)), "port", cores
 
 
-def measure_cpu_baseline(budget_s=12.0, single_thread=True):
-    """The reference's CPU qxmatch on the bounded sample: all host threads (up to three repetitions
-    inside `budget_s`), then once on one thread (SURVEY.md section 8d asks for both)."""
+def measure_cpu_baseline(budget_s=12.0, single_thread=True, full=False):
+    """The reference's CPU qxmatch on the host cores. full=True (bench default, N = 1): the WHOLE C2
+    workload (1e7 x 1e7) once on all host threads -- the same configuration the GPU number is quoted
+    on (33 s on the pool's 16-core hosts). Otherwise a bounded sample, up to three repetitions inside
+    `budget_s`. Then the sample once on one thread (SURVEY.md section 8d asks for both)."""
+    from vif_b200 import catalogs as G
     a1, b1, a2, b2, desc = cpu_sample()
     fn, kind, cores = cpu_runner()
     fn(a1[:20000], b1[:20000], a2[:20000], b2[:20000])
-    t0 = time.perf_counter()
-    reps = 0
-    while reps < 3 and time.perf_counter() - t0 < budget_s:
-        fn(a1, b1, a2, b2)
-        reps += 1
-    cdt = (time.perf_counter() - t0) / reps
-    out = {"value": SAMPLE_N / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    if full:
+        f1, g1 = G.c2(1, N_FULL)
+        f2, g2 = G.c2(2, N_FULL)
+        t0 = time.perf_counter()
+        fn(f1, g1, f2, g2)
+        cdt = time.perf_counter() - t0
+        out = {"value": N_FULL / cdt, "unit": UNIT, "cores": cores, "kind": kind, "seconds": cdt,
+               "sample": "the full workload (%d x %d rows), one run on all host threads" % (N_FULL, N_FULL)}
+        del f1, g1, f2, g2
+    else:
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 and time.perf_counter() - t0 < budget_s:
+            fn(a1, b1, a2, b2)
+            reps += 1
+        cdt = (time.perf_counter() - t0) / reps
+        out = {"value": SAMPLE_N / cdt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if single_thread and cores > 1:
-        # same sample (a smaller one is cache-friendlier: 50 000 rows run 2.8x faster per source), once
+        # a bounded sample (a smaller one is cache-friendlier: 50 000 rows run 2.8x faster per source), once
         fn1, _, _ = cpu_runner(threads=1)
         t0 = time.perf_counter()
         fn1(a1, b1, a2, b2)
         out["value_1_thread"] = SAMPLE_N / (time.perf_counter() - t0)
+        out["sample_1_thread"] = desc
     return out
 
 
 def run_reference_arm(args):
+    """The reference's own CPU qxmatch (oracle/_ref: the unmodified header compiled here) on all host
+    threads. Each step is a bounded sample of C2 (REF_ARM_N rows per catalog in a sub-box of the same
+    density) so that K + W steps end within minutes; the whole 1e7 x 1e7 workload is then run ONCE and
+    its figure reported beside the sample's (`full_size`; XM_BENCH_NO_FULL=1 skips it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    a1, b1, a2, b2, desc = cpu_sample()
+    n = min(args.n or REF_ARM_N, REF_ARM_N)
+    a1, b1, a2, b2, desc = cpu_sample(n)
     fn, kind, cores = cpu_runner()
     for _ in range(args.warmup):
         fn(a1, b1, a2, b2)
@@ -204,7 +231,16 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         fn(a1, b1, a2, b2)
     dt = (time.perf_counter() - t0) / args.steps
-    v = SAMPLE_N / dt
+    v = n / dt
+    full = None
+    if not os.environ.get("XM_BENCH_NO_FULL") and n == REF_ARM_N:
+        from vif_b200 import catalogs as G
+        f1, g1 = G.c2(1, N_FULL)
+        f2, g2 = G.c2(2, N_FULL)
+        t0 = time.perf_counter()
+        fn(f1, g1, f2, g2)
+        fdt = time.perf_counter() - t0
+        full = {"value": N_FULL / fdt, "unit": UNIT, "seconds": fdt, "rows": [N_FULL, N_FULL], "runs": 1}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
@@ -212,6 +248,7 @@ def run_reference_arm(args):
         "config": {"workload": workload_desc(N_FULL * (args.gpus if args.scaling == "weak" else 1), N_FULL), "nth": 1,
                    "sample": desc},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "full_size": full,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -232,7 +269,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
+        # stdout carries ONE JSON line: NCCL's own log (NCCL_DEBUG, whatever the launcher set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     # weak scaling (c2 default): every rank brings args.n rows of catalog 1, catalog 2 stays args.n rows
     n1 = args.n * world if args.scaling == "weak" else args.n
@@ -256,9 +294,10 @@ def run_gpu_arm(args):
     else:
         ra2 = torch.empty(n2, dtype=torch.float64, device=dev)
         dec2 = torch.empty(n2, dtype=torch.float64, device=dev)
-    params = QxmatchParams(nth=5 if args.config == "c3" else 1, device=local)
+    params = QxmatchParams(nth=5 if args.config == "c3" else 1, device=local, brute_force=(args.config == "c4"))
     stats_acc = {"ms_forward": 0.0, "ms_reverse": 0.0, "ms_search": 0.0, "ms_total": 0.0, "ms_index": 0.0,
-                 "ms_bbox": 0.0, "launches": 0, "evals": 0, "steps": 0}
+                 "ms_bbox": 0.0, "ms_filter_fwd": 0.0, "ms_filter_rev": 0.0, "launches": 0, "evals": 0, "steps": 0,
+                 "refined": 0}
 
     def step(record):
         from vif_b200.qxmatch import last_stats
@@ -277,8 +316,10 @@ def run_gpu_arm(args):
             out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
         if record:
             st = last_stats(local)
-            for k in ("ms_forward", "ms_reverse", "ms_search", "ms_total", "ms_index", "ms_bbox"):
+            for k in ("ms_forward", "ms_reverse", "ms_search", "ms_total", "ms_index", "ms_bbox", "ms_filter_fwd",
+                      "ms_filter_rev"):
                 stats_acc[k] += st[k]
+            stats_acc["refined"] += st["rows_refined_fwd"] + st["rows_refined_rev"]
             stats_acc["launches"] += st["launches"]
             stats_acc["evals"] += st["evals_fwd"] + st["evals_rev"]
             stats_acc["steps"] += 1
@@ -408,18 +449,62 @@ def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev
     return n1 / dt.item(), e2e_steps, h2d, d2h, dt
 
 
+def fp64_peak():
+    """Measured DFMA peak of this pool's B200 (scripts/fp64_peak.py -> profiles/fp64_peak.json), else nominal."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    try:
+        return float(json.load(open(p))["tflops"]), "measured (profiles/fp64_peak.json)"
+    except Exception:
+        return 37.2, "nominal (148 SM x 64 DFMA/clk x 2 x 1.965 GHz)"
+
+
+def parallelism_desc(args, world, hi, lo):
+    if world == 1:
+        return "1 rank"
+    if args.config == "c2" and args.scaling == "strong":
+        return ("catalog 2 NCCL-broadcast, catalog-1 row shards NCCL-all-gathered; each of the %d ranks matches its row "
+                "block of catalog 1 (forward) and of catalog 2 (reverse) against the whole other catalog; no merge "
+                "collective" % world)
+    return ("catalog-1 rows sharded over %d ranks (%d rows each); catalog 2 NCCL-broadcast and indexed per rank; reverse "
+            "match merged by one kernel over NVLink peer memory (xm_rev_merge_p2p; NCCL all-reduce(min) when peer "
+            "mappings are unavailable)" % (world, hi - lo))
+
+
 def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_acc, e2e_value, e2e_steps, h2d, d2h, dt):
-    if True:
-        peaks, how = measured_peaks()
-        ns = max(stats_acc["steps"], 1)
-        # dominant kernel: the ring search (forward + reverse launches, same kernel). Algorithmic
-        # bytes per launch: source coords in, candidate coords in, (id, d) out -- DESIGN.md section 5.
-        nsrc_f, ncand_f = hi - lo, n2
-        bytes_fwd = 16 * nsrc_f + 16 * ncand_f + 16 * nsrc_f
-        bytes_rev = 16 * n2 + 16 * nsrc_f + 16 * n2
-        ms_f, ms_r = stats_acc["ms_forward"] / ns, stats_acc["ms_reverse"] / ns
-        ms_s = stats_acc["ms_search"] / ns          # forward and reverse launches overlap on two streams
-        achieved = (bytes_fwd + bytes_rev) / (ms_s * 1e-3) / 1e9 if ms_s > 0 else 0.0
+    peaks, how = measured_peaks()
+    ns = max(stats_acc["steps"], 1)
+    avg = {k: stats_acc[k] / ns for k in ("ms_total", "ms_bbox", "ms_index", "ms_search", "ms_forward", "ms_reverse",
+                                           "ms_filter_fwd", "ms_filter_rev")}
+    nth = 5 if args.config == "c3" else 1
+    mirror = args.config != "c3"
+    # whole-path algorithmic bytes, SURVEY.md section 8(d): coordinates in, (id, d) out, (rid, rd) out
+    whole_bytes = 16 * n1 + (16 * n2 if args.config != "c3" else 0) + 16 * nth * n1 + (16 * n2 if mirror else 0)
+    whole_gbps = whole_bytes / (ms_step * 1e-3) / 1e9
+    if args.config == "c4":
+        peak, peak_how = fp64_peak()
+        tfl = 11.0 * n1 * n2 / (ms_step * 1e-3) / 1e12
+        roof = {"bound": "fp64", "kernel": "brute_filter_kernel (forward pass + reverse pass) + brute_refine_kernel",
+                "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": None,
+                "peak_source": peak_how,
+                "convention": "11 FP64 flop per (i, j) pair of SURVEY.md 8(d), n1*n2 pairs (the reference evaluates a "
+                              "pair once for both directions); the kernels evaluate every pair once per direction as a "
+                              "3-term dot product (1 DMUL + 2 DFMA + 1 DSETP)",
+                "dfma_issue": {"pairs_per_s_per_direction": n1 * n2 * 2.0 / (avg["ms_search"] * 1e-3) / 2.0
+                               if avg["ms_search"] > 0 else None,
+                               "fp64_instr_tflops_equiv": (2.0 * n1 * n2 * 5.0 / (avg["ms_search"] * 1e-3) / 1e12
+                                                           if avg["ms_search"] > 0 else None),
+                               "note": "2 passes x n1*n2 pairs x (1 DMUL + 2 DFMA = 5 flop) / search time; ncu "
+                                       "sm__inst_executed_pipe_fp64 of the same kernel: profiles/r2_brute_filter_ncu.txt"},
+                "stage_ms": avg}
+    else:
+        # dominant kernel: the nearest-neighbour filter (forward + reverse launches of the same kernel, run
+        # concurrently on two streams). Algorithmic bytes per launch: source coordinates in, candidate
+        # coordinates in, (id, d) out -- DESIGN.md section 5.
+        nsrc_f = hi - lo
+        bytes_fwd = 16 * nsrc_f + 16 * n2 + 16 * nth * nsrc_f
+        bytes_rev = (16 * n2 + 16 * nsrc_f + 16 * n2) if mirror else 0
+        ms_s = avg["ms_search"]
+        k_ach = (bytes_fwd + bytes_rev) / (ms_s * 1e-3) / 1e9 if ms_s > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ring_search_traffic.json")
         if os.path.exists(tp) and args.config == "c2" and world == 1 and n1 == N_FULL:
@@ -427,46 +512,48 @@ def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_ac
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        whole_bytes = 16 * n1 + 16 * n2 + 16 * n1 + 16 * n2
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(n1, n2, args.config), "n1": n1, "n2": n2, "nth": 1,
-                       "l2": "no flush: the 320 MB of input coordinates plus the ~0.5 GB cell index exceed the 126 MB L2",
-                       "parallelism": ("1 rank" if world == 1 else
-                                       ("catalog 2 NCCL-broadcast, catalog-1 row shards NCCL-all-gathered; each of the %d ranks "
-                                        "matches its row block of catalog 1 (forward) and of catalog 2 (reverse) against the "
-                                        "whole other catalog; no merge collective" % world)
-                                       if args.config == "c2" and args.scaling == "strong" else
-                                       ("catalog-1 rows sharded over %d ranks (%d rows each); catalog 2 NCCL-broadcast and "
-                                        "indexed per rank; reverse match merged by one kernel over NVLink peer memory "
-                                        "(xm_rev_merge_p2p; NCCL all-reduce(min) when peer mappings are unavailable)"
-                                        % (world, hi - lo)))},
-            "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                     "ms_per_step": dt.item() * 1e3, "steps": e2e_steps} if e2e_value is not None else None),
-            "e2e_pageable": getattr(args, "e2e_pageable", None),
-            "gpu_launches": int(launches.item()),
-            "step_ms_rank0": args.step_ms,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": ("sphere_nn_filter_kernel + list-mode sphere_search_kernel (forward and reverse lanes, concurrent)" if args.config == "c5" else
-                                                   "ring_nn_filter_kernel (forward + reverse launches, run concurrently)"), "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": traffic, "peak_source": how,
-                         "algorithmic_bytes_per_launch": {"forward": bytes_fwd, "reverse": bytes_rev},
-                         "ms_per_launch": {"forward": ms_f, "reverse": ms_r, "both_overlapped": ms_s},
-                         "whole_path": {"bytes": whole_bytes, "GBps": whole_bytes / (ms_step * 1e-3) / 1e9,
-                                        "frac": whole_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                         "stage_ms": {k: stats_acc[k] / ns for k in ("ms_total", "ms_bbox", "ms_index", "ms_search", "ms_forward", "ms_reverse")},
-                         "distance_evals_per_step": stats_acc["evals"] / ns,
-                         # the limit that actually binds: FP64/issue work of the searches, by the
-                         # 11-flop-per-evaluation convention of SURVEY.md section 8(d); nominal peak
-                         "fp64": {"achieved_tflops": 11.0 * stats_acc["evals"] / ns / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0,
-                                  "nominal_peak_tflops": 37.2}},
-        }
-        if world == 1 and not args.no_cpu and args.config == "c2":
-            line["cpu_baseline"] = measure_cpu_baseline()
-        print(json.dumps(line))
+        kname = {"c5": "sphere_nn_filter_kernel + list-mode sphere_search_kernel (forward and reverse lanes, concurrent)",
+                 "c3": "ring_topk_filter_kernel (nth = 5) + list-mode ring_search_exact_kernel"}.get(
+                     args.config, "ring_nn32_kernel (forward + reverse launches, run concurrently on two streams)")
+        roof = {"bound": "hbm", "achieved": whole_gbps, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": whole_gbps / peaks["hbm_gbs"], "traffic": traffic, "peak_source": how,
+                "what": "whole path, SURVEY.md 8(d): B = 16 n1 + 16 n2 + 16 nth n1 + 16 n2 bytes / step time",
+                "bytes": whole_bytes,
+                "dominant_kernel": {"kernel": kname, "achieved": k_ach, "frac": k_ach / peaks["hbm_gbs"], "unit": "GB/s",
+                                    "algorithmic_bytes_per_launch": {"forward": bytes_fwd, "reverse": bytes_rev},
+                                    "ms": {"forward_launch": avg["ms_filter_fwd"], "reverse_launch": avg["ms_filter_rev"],
+                                           "both_lanes_overlapped": ms_s},
+                                    "note": "achieved = bytes of both launches / time the two search lanes are in flight "
+                                            "(they overlap; each launch's own CUDA-event time is listed; traffic = "
+                                            "dram bytes of ONE launch from ncu, profiles/ring_search_traffic.json)"},
+                "stage_ms": avg,
+                "distance_evals_per_step": stats_acc["evals"] / ns,
+                "rows_to_exact_kernel_per_step": stats_acc["refined"] / ns,
+                # the limit that actually binds is issue/latency, not bytes: evaluations by the 11-flop convention
+                "fp64": {"achieved_tflops": 11.0 * stats_acc["evals"] / ns / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0,
+                         "peak_tflops": fp64_peak()[0], "peak_source": fp64_peak()[1],
+                         "note": "the filter evaluates in FP32 (4 FFMA/FMUL per pair); FP64 only for the winner"}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(n1, n2, args.config), "n1": n1, "n2": n2, "nth": nth,
+                   "l2": ("no flush: the input coordinates plus the cell index exceed the 126 MB L2" if args.config != "c4" else
+                          "no flush: the kernel is FP64-pipe bound; its candidate tiles are staged by TMA from L2"),
+                   "parallelism": parallelism_desc(args, world, hi, lo)},
+        "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                 "ms_per_step": dt.item() * 1e3, "steps": e2e_steps} if e2e_value is not None else None),
+        "e2e_pageable": getattr(args, "e2e_pageable", None),
+        "gpu_launches": int(launches.item()),
+        "step_ms_rank0": args.step_ms,
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if getattr(args, "c5_strong", None) is not None:
+        line["c5_strong"] = args.c5_strong
+    if world == 1 and not args.no_cpu and args.config == "c2":
+        line["cpu_baseline"] = measure_cpu_baseline(full=(n1 == N_FULL and not os.environ.get("XM_BENCH_NO_FULL")))
+    print(json.dumps(line))
 
 
 def main():
@@ -477,8 +564,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", dest="n", type=int, default=None, help="rows of catalog 1 (default: the full workload)")
     ap.add_argument("--rows2", dest="n2", type=int, default=None, help="rows of catalog 2 (default: n for c2, n/10 for c5)")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
-                    help="c2 = the headline metric's workload (default); c5 = 1e9 x 1e8 full sky (manual scaling runs)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = the headline metric's workload (default); c3 = self nth=5 clustered; c4 = brute force "
+                         "1e6 x 1e6 full sky (FP64 roofline); c5 = 1e9 x 1e8 full sky")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="N>1: weak = every rank brings --rows rows of catalog 1 against the same catalog 2 (c2 default: "
                          "the path shards by catalog-1 rows); strong = the total stays --rows (c3/c5 default)")
@@ -486,11 +574,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.n is None:
-        args.n = {"c5": 1_000_000_000, "c3": 100_000_000}.get(args.config, N_FULL)
+        args.n = {"c5": 1_000_000_000, "c3": 100_000_000, "c4": C4_N}.get(args.config, N_FULL)
     if args.scaling == "auto":
         args.scaling = "weak" if args.config == "c2" else "strong"
-    if args.config == "c3":
-        args.no_e2e = True
+    if args.config in ("c3", "c4"):
+        args.no_e2e = args.no_e2e or args.config == "c3"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -126,6 +126,7 @@ namespace astro {
         }
 
         xm_params p = xm_params();
+        p.struct_size = sizeof(xm_params);
         p.thread = params.thread; p.nth = nth;
         p.verbose = params.verbose; p.self = params.self; p.brute_force = params.brute_force;
         p.no_mirror = params.no_mirror; p.linear = params.linear;

@@ -59,6 +59,10 @@ enum {
 
 /* Mirrors vif::astro::qxmatch_params (qxmatch.hpp:31-39) field for field, then GPU extras. */
 typedef struct xm_params {
+    uint64_t struct_size;             /* sizeof(xm_params) as compiled into the CALLER (XM_PARAMS_INIT sets */
+                                      /* it). The library reads that many bytes and takes every field the   */
+                                      /* caller does not know as zero, so callers built against an older    */
+                                      /* header keep working; 0 or a size it does not know is rejected.     */
     uint64_t thread;                  /* ignored by the GPU path                                   */
     uint64_t nth;                     /* clamped to >= 1 (qxmatch.hpp:152)                         */
     uint8_t  verbose;
@@ -86,6 +90,8 @@ typedef struct xm_params {
     double   bbox1[4];                /* ra_min, ra_max, dec_min, dec_max                          */
     uint64_t fwd_begin, fwd_count, rev_begin, rev_count;
 } xm_params;
+/* xm_params p = XM_PARAMS_INIT;  -- every field zero (= reference behaviour) except the size */
+#define XM_PARAMS_INIT { sizeof(xm_params) }
 
 /* Grid geometry chosen for the cell-binned path (qxmatch.hpp:232-267), reported for inspection. */
 typedef struct xm_grid {
@@ -97,6 +103,7 @@ typedef struct xm_grid {
 
 /* Per-call statistics of the last call made on a device (device-side times from CUDA events). */
 typedef struct xm_stats {
+    uint64_t struct_size;              /* in: sizeof(xm_stats) of the caller; out: bytes the library filled */
     xm_grid  grid;
     double   ms_total;                 /* whole device pipeline                                    */
     double   ms_bbox, ms_keys, ms_sort, ms_index, ms_forward, ms_reverse;
@@ -108,7 +115,17 @@ typedef struct xm_stats {
     uint64_t evals_fwd, evals_rev;     /* distance evaluations (filter + exact)                    */
     uint64_t sin_model;                /* 1 = glibc FMA Taylor model, 2 = non-FMA model            */
     double   ms_host;                  /* host wall clock of the whole call (incl. copies)         */
+    double   ms_filter_fwd;            /* the nearest-neighbour filter kernel alone (one launch), forward   */
+    double   ms_filter_rev;            /* ... reverse; the two launches overlap in time on two streams      */
+    uint64_t cos_model;                /* 1/2 = glibc cos restated on the device (FMA / non-FMA build), 0 = */
+                                       /* CUDA libm cos (host libm not recognised: see rows_ambiguous)      */
 } xm_stats;
+
+/* DFMA micro-benchmark: the FP64 roofline denominator of the brute-force path (BASELINE.md section 2:
+ * "must be measured"). Runs `reps` launches of a kernel whose every thread carries 8 independent
+ * chains of 4096 DFMAs (grid = 8 CTAs of 256 threads per SM), times them with CUDA events and
+ * returns the best launch in *tflops (2 flop per DFMA). device = -1 -> current. */
+int32_t xm_fp64_peak(int32_t device, int32_t reps, double* tflops, char* errbuf, uint64_t errcap);
 
 /* Library / ABI version string, e.g. "vif_b200_qxmatch 0.1 (sm_100a)". Never fails. */
 const char* xm_version(void);

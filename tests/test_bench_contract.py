@@ -21,7 +21,7 @@ def _run(*args, env=None):
 
 
 def test_reference_arm_prints_one_contract_line():
-    lines = [l for l in _run("--impl", "reference", "--steps", "1", "--warmup", "0").splitlines() if l.strip()]
+    lines = [l for l in _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--rows", "100000").splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert KEYS <= set(d)
@@ -33,7 +33,7 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_reference_arm_other_ranks_are_silent():
-    assert _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--gpus", "2",
+    assert _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--gpus", "2", "--rows", "100000",
                 env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
 
 
@@ -57,4 +57,17 @@ def test_gpu_bench_line_has_roofline_and_e2e():
     assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and 0 < r["frac"] < 1 and r["unit"] == "GB/s"
+    assert abs(r["achieved"] - r["bytes"] / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]     # whole path, SURVEY 8(d)
+    k = r["dominant_kernel"]
+    assert 0 < k["frac"] < 1 and k["ms"]["forward_launch"] > 0 and k["ms"]["reverse_launch"] > 0
     assert d["clocks"] is not None and d["step_ms_rank0"]["min"] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_bench_c4_line_reports_the_fp64_roofline():
+    lines = [l for l in _run("--config", "c4", "--steps", "2", "--warmup", "3", "--rows", "200000", "--no-e2e").splitlines()
+             if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    r = d["roofline"]
+    assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and r["achieved"] > 0 and r["peak"] > 10

@@ -13,11 +13,15 @@ XM_OK, XM_ERR_INVALID_ARG, XM_ERR_NONFINITE_1, XM_ERR_NONFINITE_2, XM_ERR_GRID_T
 
 
 class XmParams(C.Structure):
-    _fields_ = [("thread", u64), ("nth", u64), ("verbose", C.c_uint8), ("self", C.c_uint8),
+    _fields_ = [("struct_size", u64), ("thread", u64), ("nth", u64), ("verbose", C.c_uint8), ("self", C.c_uint8),
                 ("brute_force", C.c_uint8), ("no_mirror", C.c_uint8), ("linear", C.c_uint8),
                 ("has_bbox1", C.c_uint8), ("exact_only", C.c_uint8), ("exact_grid", C.c_uint8),
                 ("device", i32), ("has_ranges", i32), ("bbox1", f64 * 4),
                 ("fwd_begin", u64), ("fwd_count", u64), ("rev_begin", u64), ("rev_count", u64)]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.struct_size = C.sizeof(XmParams)
 
 
 class XmGrid(C.Structure):
@@ -29,20 +33,25 @@ class XmGrid(C.Structure):
 
 
 class XmStats(C.Structure):
-    _fields_ = [("grid", XmGrid), ("ms_total", f64), ("ms_bbox", f64), ("ms_keys", f64),
+    _fields_ = [("struct_size", u64), ("grid", XmGrid), ("ms_total", f64), ("ms_bbox", f64), ("ms_keys", f64),
                 ("ms_sort", f64), ("ms_index", f64), ("ms_forward", f64), ("ms_reverse", f64),
                 ("ms_search", f64), ("launches", u64), ("rows_refined_fwd", u64),
                 ("rows_refined_rev", u64), ("rows_ambiguous", u64), ("evals_fwd", u64),
-                ("evals_rev", u64), ("sin_model", u64), ("ms_host", f64)]
+                ("evals_rev", u64), ("sin_model", u64), ("ms_host", f64), ("ms_filter_fwd", f64), ("ms_filter_rev", f64),
+                ("cos_model", u64)]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.struct_size = C.sizeof(XmStats)
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "grid"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("grid", "struct_size")}
         d["grid"] = self.grid.as_dict()
         return d
 
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
-SYMBOLS = ["xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
+SYMBOLS = ["xm_fp64_peak", "xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
            "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
@@ -76,6 +85,8 @@ def load():
     lib.xm_grid_from_bbox.argtypes = [dp, dp, u64, u64, i32, C.POINTER(XmGrid)]
     lib.xm_bbox_dev.restype = i32
     lib.xm_bbox_dev.argtypes = [vp, vp, u64, i32, vp, dp, up, C.c_char_p, u64]
+    lib.xm_fp64_peak.restype = i32
+    lib.xm_fp64_peak.argtypes = [i32, i32, C.POINTER(f64), C.c_char_p, u64]
     lib.xm_last_stats.restype = i32
     lib.xm_last_stats.argtypes = [i32, C.POINTER(XmStats)]
     lib.xm_sort_pairs_dev.restype = i32

@@ -1,12 +1,13 @@
 // C ABI + host orchestration of the device pipeline (see include/vif_b200_qxmatch.h).
 //
-// Pipeline of one call (cell-binned path):
+// Pipeline of one call (cell-binned path), two stream lanes:
 //   bbox(cat1), bbox(cat2)            -> 10 scalars D2H, host geometry (xm_geometry.cpp)
-//   per catalog: keys -> radix sort -> cell ranges + gather to cell-ordered SoA
-//   forward ring search (cat1 rows over cat2 cells), reverse ring search (cat2 rows over cat1)
+//   lane 1: index of catalog 1 (count -> scan -> place), lane 2: index of catalog 2
+//   lane 1: forward search (filter kernel -> unpack || exact list kernel), lane 2: reverse search
 // There is no CPU fallback anywhere in this file: without a usable device every entry point
 // returns XM_ERR_CUDA.
 #include <chrono>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,7 +21,17 @@
 
 namespace xm {
 
+namespace {
+// Set by fail()/fail_cuda(): an entry point is unwinding with work possibly still in flight on the
+// library's other streams. The first scratch buffer released after that waits for the whole device
+// before it hands memory back to the pool (an error return must not let kernels of the
+// second lane write into memory the pool may give to the next call).
+thread_local bool t_error_pending = false;
+thread_local cudaMemPool_t t_pool = nullptr;      // private pool of the context the thread is working in
+}  // namespace
+
 int32_t fail_cuda(Error& err, cudaError_t e, const char* what, const char* file, int line) {
+    t_error_pending = true;
     err.code = XM_ERR_CUDA;
     snprintf(err.msg, sizeof(err.msg), "CUDA error %d (%s) in %s at %s:%d", (int)e,
              cudaGetErrorString(e), what, file, line);
@@ -28,6 +39,7 @@ int32_t fail_cuda(Error& err, cudaError_t e, const char* what, const char* file,
 }
 
 int32_t fail(Error& err, int32_t code, const char* fmt, ...) {
+    t_error_pending = true;
     err.code = code;
     va_list ap;
     va_start(ap, fmt);
@@ -51,11 +63,14 @@ struct Context {
     SearchCounters*     h_ctr = nullptr;     // pinned
     xm_stats     last;
     cudaEvent_t  ev[10];
+    cudaEvent_t  kev[4];                     // filter kernel alone: forward begin/end, reverse begin/end
     // host-buffer calls: results leave over PCIe as soon as their lane is done (copy stream), the
     // forward results while the reverse search is still running
     cudaStream_t copy = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};   // exact kernel of the undecided rows, one per lane
     cudaEvent_t  lane_ev[4];
+    cudaMemPool_t pool = nullptr;            // private stream-ordered pool: scratch of every call
+    int          cos_model = 0;
     struct HostOut { uint64_t* id = nullptr; double* d = nullptr; uint64_t* rid = nullptr; double* rd = nullptr; bool done = false; } host_out;
 };
 
@@ -94,14 +109,24 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
     XM_CUDA_TRY(cudaMalloc(&c->d_ctr, sizeof(SearchCounters)));
     XM_CUDA_TRY(cudaMallocHost(&c->h_ctr, sizeof(SearchCounters)));
     for (auto& e : c->ev) XM_CUDA_TRY(cudaEventCreate(&e));
-    // freed scratch stays in the stream-ordered pool: repeated calls never go back to the driver for
-    // memory (measured on 1e9 x 1e8: index build 60 ms with the pool warm, 230 ms when the pool had
-    // to re-map its ~80 GB every call). xm_release_memory() / XM_POOL_KEEP_GB bound the footprint.
-    cudaMemPool_t pool;
-    XM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = ~0ull;
-    if (const char* e = getenv("XM_POOL_KEEP_GB")) keep = (uint64_t)strtoull(e, nullptr, 10) << 30;
-    XM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    for (auto& e : c->kev) XM_CUDA_TRY(cudaEventCreate(&e));
+    // Scratch comes from a pool of the library's own (not the device's default pool: its release
+    // threshold is process-wide state other cudaMallocAsync users would inherit). Freed scratch
+    // stays cached there: repeated calls never go back to the driver for memory (measured on
+    // 1e9 x 1e8: index build 60 ms with the pool warm, 230 ms when it had to re-map its ~80 GB every
+    // call). xm_release_memory() / XM_POOL_KEEP_GB bound the footprint; xm_shutdown destroys the pool.
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        XM_CUDA_TRY(cudaMemPoolCreate(&c->pool, &props));
+        uint64_t keep = ~0ull;
+        if (const char* e = getenv("XM_POOL_KEEP_GB")) keep = (uint64_t)strtoull(e, nullptr, 10) << 30;
+        XM_CUDA_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c->sin_model = calibrate_sin_model();
     XM_CUDA_TRY(cudaSetDevice(prev));
     *out = c.get();
@@ -113,13 +138,40 @@ int32_t get_context(int32_t device, Context** out, Error& err) {
 struct Scratch {
     void* p = nullptr;
     cudaStream_t s = nullptr;
-    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    ~Scratch() {
+        if (!p) return;
+        if (t_error_pending) { cudaDeviceSynchronize(); cudaGetLastError(); t_error_pending = false; }
+        cudaFreeAsync(p, s);
+    }
     cudaError_t alloc(size_t bytes, cudaStream_t st) {
         s = st;
+        if (t_pool) return cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, t_pool, st);
         return cudaMallocAsync(&p, bytes ? bytes : 16, st);
     }
     template <class T> T* as() const { return (T*)p; }
 };
+
+// per-device serialisation of the entry points + the thread's scratch pool / error state
+struct CtxLock {
+    std::lock_guard<std::mutex> lk;
+    explicit CtxLock(Context* c) : lk(c->mu) { t_pool = c->pool; t_error_pending = false; }
+    ~CtxLock() { t_pool = nullptr; }
+};
+
+// Callers compiled against an older header pass a shorter xm_params (struct_size): fields they do not
+// know are zero = reference behaviour.
+int32_t normalize_params(const xm_params* in, xm_params* out, Error& err) {
+    if (!in) return fail(err, XM_ERR_INVALID_ARG, "params is NULL");
+    const uint64_t sz = in->struct_size;
+    if (sz < offsetof(xm_params, has_bbox1) || sz > sizeof(xm_params))
+        return fail(err, XM_ERR_INVALID_ARG, "xm_params.struct_size = %llu: set it to sizeof(xm_params) (XM_PARAMS_INIT); "
+                    "this library knows sizes %zu..%zu", (unsigned long long)sz, offsetof(xm_params, has_bbox1),
+                    sizeof(xm_params));
+    memset(out, 0, sizeof(*out));
+    memcpy(out, in, (size_t)sz);
+    out->struct_size = sizeof(xm_params);
+    return XM_OK;
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -514,6 +566,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             if ((rc = launch_fill_outputs(id, d, nth*n1o, linear ? dinf : dnan, s, err, &launches))) return rc;
         }
         // ---- forward search (lane s) ----
+        bool timed_f = false, timed_r = false;
         Scratch refine, resrec, plans;
         if (srcF->n == 0) {
             // empty block: nothing to match
@@ -526,7 +579,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                 XM_CUDA_TRY(plans.alloc(nn32_plan_bytes(n1o, g.nra, tile), s));
                 if ((rc = launch_ring_nn32(g, *srcF, *v2, self, tile, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
-                                           &launches))) return rc;
+                                           &launches, ctx->kev[0], ctx->kev[1]))) return rc;
+                timed_f = true;
             } else {
                 XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
                 if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
@@ -571,7 +625,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                         XM_CUDA_TRY(plans2.alloc(nn32_plan_bytes(n2o, g.nra, tile), s2));
                         if ((rc = launch_ring_nn32(g, *srcR, s1.view, false, tile, rid, rd, resrec2.p, plans2.p,
                                                    refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
-                                                   s2, ctx->lane_ev[2], err, &launches))) return rc;
+                                                   s2, ctx->lane_ev[2], err, &launches, ctx->kev[2], ctx->kev[3]))) return rc;
+                        timed_r = true;
                     } else {
                         XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
                         if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,
@@ -617,6 +672,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         st.ms_forward = ev_ms(ev[5], ev[6]);
         st.ms_reverse = ev_ms(ev[9], ev[7]);           // runs concurrently with the forward search
         st.ms_search = ev_ms(ev[5], ev[8]);
+        if (timed_f) st.ms_filter_fwd = ev_ms(ctx->kev[0], ctx->kev[1]);
+        if (timed_r) st.ms_filter_rev = ev_ms(ctx->kev[2], ctx->kev[3]);
     }
 finish:
     if (sphere_done) {
@@ -675,7 +732,6 @@ void copy_err(const Error& err, char* errbuf, uint64_t errcap) {
 int32_t check_args(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,
                    const double* dec2, uint64_t n2, const xm_params* p, uint64_t* id, double* d,
                    uint64_t* rid, double* rd, Error& err) {
-    if (!p) return fail(err, XM_ERR_INVALID_ARG, "params is NULL");
     if ((n1 && (!ra1 || !dec1)) || (n2 && (!ra2 || !dec2)))
         return fail(err, XM_ERR_INVALID_ARG, "NULL coordinate pointer");
     if (n1 && (!id || !d)) return fail(err, XM_ERR_INVALID_ARG, "NULL id/d output pointer");
@@ -693,7 +749,7 @@ int32_t dist_entry(int32_t device, void* stream, char* errbuf, uint64_t errcap, 
     if (!rc) rc = get_context(device, &ctx, err);
     if (!rc) {
         auto body = [&]() -> int32_t {
-            std::lock_guard<std::mutex> lk(ctx->mu);
+            CtxLock lk(ctx);
             DeviceGuard dg;
             XM_CUDA_TRY(dg.set(ctx->device));
             cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -732,6 +788,7 @@ void xm_shutdown(void) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         for (auto& e : c->ev) cudaEventDestroy(e);
+        for (auto& e : c->kev) cudaEventDestroy(e);
         for (auto& e : c->sync_ev) cudaEventDestroy(e);
         cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2);
         cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy);
@@ -740,6 +797,7 @@ void xm_shutdown(void) {
         cudaFree(c->d_small); cudaFreeHost(c->h_small);
         cudaFree(c->d_ctr); cudaFreeHost(c->h_ctr);
         cudaStreamDestroy(c->stream);
+        if (c->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(c->pool); }
     }
     g_ctx.clear();
     stage_shutdown();
@@ -749,12 +807,23 @@ int32_t xm_release_memory(int32_t device) {
     int prev = 0;
     if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return XM_ERR_CUDA; }
     if (device < 0) device = prev;
-    cudaMemPool_t pool;
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_ctx.find(device);
+        if (it != g_ctx.end()) pool = it->second->pool;
+    }
+    if (!pool) return XM_OK;                  // nothing allocated on that device yet
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
-              cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && cudaMemPoolTrimTo(pool, 0) == cudaSuccess;
+              cudaMemPoolTrimTo(pool, 0) == cudaSuccess;
     if (!ok) cudaGetLastError();
     cudaSetDevice(prev);
     return ok ? XM_OK : XM_ERR_CUDA;
+}
+
+int32_t xm_fp64_peak(int32_t device, int32_t reps, double* tflops, char* errbuf, uint64_t errcap) {
+    return dist_entry(device, nullptr, errbuf, errcap, !tflops,
+                      [&](Context*, cudaStream_t s, Error& err) { return launch_fp64_peak(reps, tflops, s, err); });
 }
 
 int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const double* ra2,
@@ -762,11 +831,14 @@ int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const
                        double* d, uint64_t* rid, double* rd, void* stream, char* errbuf,
                        uint64_t errcap) {
     Error err;
-    int32_t rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
+    xm_params pn;
+    int32_t rc = normalize_params(params, &pn, err);
+    params = &pn;
+    if (!rc) rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
     Context* ctx = nullptr;
     if (!rc) rc = get_context(params->device, &ctx, err);
     if (!rc) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        CtxLock lk(ctx);
         DeviceGuard dg;
         cudaError_t e = dg.set(ctx->device);
         if (e != cudaSuccess) rc = fail_cuda(err, e, "cudaSetDevice", __FILE__, __LINE__);
@@ -775,7 +847,7 @@ int32_t xm_qxmatch_dev(const double* ra1, const double* dec1, uint64_t n1, const
             const auto t0 = std::chrono::steady_clock::now();
             rc = run_device(ctx, s, ra1, dec1, n1, ra2, dec2, n2, *params, id, d, rid, rd, err);
             ctx->last.ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            if (rc == XM_ERR_CUDA) { cudaStreamSynchronize(s); cudaGetLastError(); }
+            if (rc != XM_OK) { cudaDeviceSynchronize(); cudaGetLastError(); }   // nothing of this call stays in flight
         }
     }
     if (rc) copy_err(err, errbuf, errcap);
@@ -786,14 +858,17 @@ int32_t xm_qxmatch_f64(const double* ra1, const double* dec1, uint64_t n1, const
                        const double* dec2, uint64_t n2, const xm_params* params, uint64_t* id,
                        double* d, uint64_t* rid, double* rd, char* errbuf, uint64_t errcap) {
     Error err;
-    int32_t rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
+    xm_params pn;
+    int32_t rc = normalize_params(params, &pn, err);
+    params = &pn;
+    if (!rc) rc = check_args(ra1, dec1, n1, ra2, dec2, n2, params, id, d, rid, rd, err);
     if (!rc && params->has_ranges) rc = fail(err, XM_ERR_INVALID_ARG, "row ranges need the device entry point (xm_qxmatch_dev)");
     Context* ctx = nullptr;
     if (!rc) rc = get_context(params->device, &ctx, err);
     if (rc) { copy_err(err, errbuf, errcap); return rc; }
 
     auto body = [&]() -> int32_t {
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        CtxLock lk(ctx);
         DeviceGuard dg;
         XM_CUDA_TRY(dg.set(ctx->device));
         cudaStream_t s = ctx->stream;
@@ -873,7 +948,7 @@ int32_t xm_bbox_dev(const double* ra, const double* dec, uint64_t n, int32_t dev
     if (!rc) rc = get_context(device, &ctx, err);
     if (!rc) {
         auto body = [&]() -> int32_t {
-            std::lock_guard<std::mutex> lk(ctx->mu);
+            CtxLock lk(ctx);
             DeviceGuard dg;
             XM_CUDA_TRY(dg.set(ctx->device));
             cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -899,8 +974,11 @@ int32_t xm_last_stats(int32_t device, xm_stats* out) {
     Context* ctx = nullptr;
     int32_t rc = get_context(device, &ctx, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    *out = ctx->last;
+    CtxLock lk(ctx);
+    const uint64_t want = out->struct_size;
+    if (want < sizeof(uint64_t) || want > (1u << 20)) return XM_ERR_INVALID_ARG;   // caller did not set struct_size
+    ctx->last.struct_size = want < sizeof(xm_stats) ? want : sizeof(xm_stats);
+    memcpy(out, &ctx->last, (size_t)ctx->last.struct_size);
     return XM_OK;
 }
 
@@ -912,7 +990,7 @@ int32_t xm_sort_pairs_dev(uint32_t* keys, uint32_t* vals, uint64_t n, int32_t ke
     if (!rc) rc = get_context(device, &ctx, err);
     if (!rc) {
         auto body = [&]() -> int32_t {
-            std::lock_guard<std::mutex> lk(ctx->mu);
+            CtxLock lk(ctx);
             DeviceGuard dg;
             XM_CUDA_TRY(dg.set(ctx->device));
             cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -1029,7 +1107,7 @@ int32_t xm_clean_best_dev(const uint64_t* id, const uint64_t* rid, uint64_t n1, 
     if (!rc) rc = get_context(device, &ctx, err);
     if (!rc) {
         auto body = [&]() -> int32_t {
-            std::lock_guard<std::mutex> lk(ctx->mu);
+            CtxLock lk(ctx);
             DeviceGuard dg;
             XM_CUDA_TRY(dg.set(ctx->device));
             cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;

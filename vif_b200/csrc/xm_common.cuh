@@ -89,6 +89,9 @@ size_t  qdist_scratch_bytes(uint64_t n);
 int32_t launch_qdist(const double* ra, const double* dec, uint64_t n, int model, void* scratch, double* out,
                      cudaStream_t s, Error& err);
 
+// xm_peak.cu
+int32_t launch_fp64_peak(int reps, double* tflops, cudaStream_t s, Error& err);
+
 // pageable host buffers (xm_staging.cu)
 struct StageJob { void* dev; void* host; size_t bytes; };
 bool    host_pointer_is_pageable(const void* p);
@@ -149,7 +152,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
                          uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                          uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                          SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
-                         uint64_t* launches);
+                         uint64_t* launches, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,

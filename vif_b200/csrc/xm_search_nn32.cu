@@ -474,7 +474,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
                          uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                          uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                          SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
-                         uint64_t* launches) {
+                         uint64_t* launches, cudaEvent_t k0, cudaEvent_t k1) {
     if (src.n == 0) return XM_OK;
     const uint32_t ntiles = src.n/(uint32_t)tile + g.nra + 1;
     TilePlan32* plan = (TilePlan32*)plan_scratch;
@@ -489,11 +489,13 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
     uint32_t ahead = 148u*4u;
     if (const char* e = getenv("XM_NN32_AHEAD")) ahead = (uint32_t)atoi(e);
     if (ahead == 0) ahead = ntiles;
+    if (k0) XM_CUDA_TRY(cudaEventRecord(k0, s));
     if (self) ring_nn32_kernel<true><<<ntiles, tile, 0, s>>>(g, src, cand, plan, res, refine_list, refine_count,
                                                               reverse ? 1 : 0, ctr, ntiles, ahead);
     else ring_nn32_kernel<false><<<ntiles, tile, 0, s>>>(g, src, cand, plan, res, refine_list, refine_count,
                                                           reverse ? 1 : 0, ctr, ntiles, ahead);
     *launches += 2;
+    if (k1) XM_CUDA_TRY(cudaEventRecord(k1, s));
     if (filter_done) XM_CUDA_TRY(cudaEventRecord(filter_done, s));
     int32_t rc = launch_unpack_results(result_scratch, src.n, id_out, d_out, s, err, launches);
     if (rc) return rc;
