@@ -259,7 +259,7 @@ def run_gpu_arm(args):
     from vif_b200 import catalogs as G
     from vif_b200 import qxmatch
     from vif_b200.qxmatch import QxmatchParams
-    from vif_b200.distributed import qxmatch_sharded, qxmatch_partitioned, shard_bounds
+    from vif_b200.distributed import qxmatch_sharded, qxmatch_partitioned, qxmatch_banded, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -312,6 +312,10 @@ def run_gpu_arm(args):
         elif args.config == "c2" and args.scaling == "strong":
             # fixed 1e7 x 1e7: catalogs small enough to replicate, row blocks of BOTH per rank, no merge
             out = qxmatch_partitioned(ra1, dec1, ra2, dec2, lo, n1, params)
+        elif args.config == "c5" and not os.environ.get("XM_C5_SHARDED"):
+            # both directions sharded: declination bands, one all-to-all of catalog 1 over NVLink
+            fwd, _, rev = qxmatch_banded(ra1, dec1, ra2, dec2, lo, params, home=bool(os.environ.get("XM_C5_HOME")))
+            out = (fwd, rev)
         else:
             out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
         if record:
@@ -465,6 +469,11 @@ def parallelism_desc(args, world, hi, lo):
         return ("catalog 2 NCCL-broadcast, catalog-1 row shards NCCL-all-gathered; each of the %d ranks matches its row "
                 "block of catalog 1 (forward) and of catalog 2 (reverse) against the whole other catalog; no merge "
                 "collective" % world)
+    if args.config == "c5" and not os.environ.get("XM_C5_SHARDED"):
+        return ("catalog 2 NCCL-broadcast; catalog-1 rows (%d per rank) regrouped into %d equal-area declination bands by one "
+                "NCCL all-to-all over NVLink (order-preserving partition kernel, halo rows to both sides); rank b matches "
+                "band b in both directions; results stay with the band, keyed by global row (XM_C5_HOME=1: forward results "
+                "return to the rows' owners by a second all-to-all)" % (hi - lo, world))
     return ("catalog-1 rows sharded over %d ranks (%d rows each); catalog 2 NCCL-broadcast and indexed per rank; reverse "
             "match merged by one kernel over NVLink peer memory (xm_rev_merge_p2p; NCCL all-reduce(min) when peer "
             "mappings are unavailable)" % (world, hi - lo))

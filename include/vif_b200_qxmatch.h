@@ -121,6 +121,30 @@ typedef struct xm_stats {
                                        /* CUDA libm cos (host libm not recognised: see rows_ambiguous)      */
 } xm_stats;
 
+/* Order-preserving declination-band partition of a device-resident catalog: the exchange step of the
+ * spatially decomposed multi-GPU search (vif_b200.distributed.qxmatch_banded; replaces the row chunks of
+ * qxmatch.hpp:422-454 where a chunk would have to meet the whole other catalog). Band b owns
+ * [edges[b], edges[b+1]) (nb + 1 ascending edges [deg] enclosing every dec); a row within `halo` [deg]
+ * of an edge is also emitted for the band beyond it. out receives *total triples {ra, dec, bits} grouped
+ * by destination band, rows ascending inside a band; bits (read the double as u64) = row0 + row, with
+ * bit 63 set when the band is the row's own (primary) one. counts[nb] (device) = triples per band.
+ * only >= 0 emits that band alone (selection of one band + halo out of a replicated catalog).
+ * cap = triples `out` can hold (n + the halo rows; the call fails when it does not suffice). */
+int32_t xm_band_partition_dev(const double* ra, const double* dec, uint64_t n, uint64_t row0, const double* edges,
+                              int32_t nb, double halo, int32_t only, double* out, uint64_t cap, uint64_t* counts,
+                              uint64_t* total, int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
+/* After the band x band search of qxmatch_banded. xm_band_finish_dev: id_io[j] (index into the band's
+ * candidate array, -1 = none) becomes the candidate's GLOBAL row (bits_cand = third column of its triples,
+ * contiguous); *bad (device u64, accumulated) counts primary rows (bit 63 of bits_src[j]) whose distance is
+ * not below hlim [arcsec]: their neighbour may lie outside the band. xm_band_home_dev: results that
+ * travelled back to the rows' owner rank -- got = m pairs {id bits, d} in the order of the m triples
+ * `sent` this rank emitted; entries of primary triples are stored at row - row0 of id_out / d_out. */
+int32_t xm_band_finish_dev(int64_t* id_io, const double* d, const int64_t* bits_src, const int64_t* bits_cand, uint64_t n,
+                           double hlim, uint64_t* bad, int32_t device, void* stream, char* errbuf, uint64_t errcap);
+int32_t xm_band_home_dev(const double* got, const double* sent, uint64_t m, uint64_t row0, int64_t* id_out, double* d_out,
+                         int32_t device, void* stream, char* errbuf, uint64_t errcap);
+
 /* DFMA micro-benchmark: the FP64 roofline denominator of the brute-force path (BASELINE.md section 2:
  * "must be measured"). Runs `reps` launches of a kernel whose every thread carries 8 independent
  * chains of 4096 DFMAs (grid = 8 CTAs of 256 threads per SM), times them with CUDA events and

@@ -37,6 +37,38 @@ for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 1
     if rank == 0:
         print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
     ok_all &= bool(flag.item())
+# declination-band decomposition (qxmatch_banded): both directions sharded; must equal the single-GPU exact search
+from vif_b200.distributed import qxmatch_banded
+for name, n1, n2, halo in (("banded", 2_000_000, 1_000_000, None), ("banded_dups", 600_000, 500_000, None),
+                           ("banded_fallback", 300_000, 200_000, 0.002)):
+    full1 = G.fullsky(1, n1, xp="torch", device=dev)
+    full2 = G.fullsky(2, n2, xp="torch", device=dev)
+    if name == "banded_dups":            # identical points inside and across the catalogs: ties go to the smallest row
+        full1 = (torch.cat((full1[0][:n1//2], full1[0][:n1//2])), torch.cat((full1[1][:n1//2], full1[1][:n1//2])))
+        full2[0][:1000] = full1[0][:1000]; full2[1][:1000] = full1[1][:1000]
+    lo, hi = shard_bounds(n1, world, rank)
+    ra2 = full2[0].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    dec2 = full2[1].clone() if rank == 0 else torch.zeros(n2, dtype=torch.float64, device=dev)
+    ident, d, rev = qxmatch_banded(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2, dec2, lo,
+                                   QxmatchParams(device=local), halo_deg=halo)
+    _, _, full = qxmatch_banded(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2, dec2, lo,
+                                QxmatchParams(device=local), halo_deg=halo, gather_reverse=True, broadcast_cat2=False)
+    ref = qxmatch(full1[0], full1[1], full2[0], full2[1], device=local, brute_force=True, exact_grid=True)
+    fwd, _, _ = qxmatch_banded(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2, dec2, lo,
+                               QxmatchParams(device=local), halo_deg=halo, home=False, broadcast_cat2=False)
+    k, k1 = rev["primary"], fwd["primary"]
+    ok = torch.equal(ident, ref.id[:, lo:hi]) and torch.equal(d, ref.d[:, lo:hi])
+    ok = ok and torch.equal(rev["rid"][k], ref.rid[rev["rows"][k]]) and torch.equal(rev["rd"][k], ref.rd[rev["rows"][k]])
+    ok = ok and torch.equal(full["rid"], ref.rid) and torch.equal(full["rd"], ref.rd)
+    ok = ok and torch.equal(fwd["id"][k1], ref.id[0][fwd["rows"][k1]]) and torch.equal(fwd["d"][k1], ref.d[0][fwd["rows"][k1]])
+    cnt = torch.tensor([int(k.sum())], device=dev)
+    dist.all_reduce(cnt)
+    ok = ok and int(cnt.item()) == n2
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
+    ok_all &= bool(flag.item())
 # partitioned run (replicated catalogs, row blocks of both): must equal the single-GPU result
 from vif_b200.distributed import qxmatch_partitioned
 for name, n1, n2 in (("partitioned", 300_001, 250_003), ("partitioned_even", 200_000, 100_000)):

@@ -102,3 +102,84 @@ def test_reverse_merge_ties_pick_smallest_row(tmp_path, oracle):
     b1 = np.concatenate([b2[:10], b2[:10]])
     exp = oracle.oracle_qxmatch(a1, b1, a2, b2, brute_force=True)
     assert np.all(exp["rid"] < 10)
+
+
+# ---- declination-band decomposition (qxmatch_banded) ----------------------------------------------------
+def _np_partition(ra, dec, row0, edges, halo, only):
+    """numpy stand-in of xm_band_partition_dev (same contract: order preserving, halo rows to both sides)."""
+    ra, dec = ra.numpy(), dec.numpy()
+    nb = len(edges) - 1
+    b = np.searchsorted(edges, dec, side="right") - 1
+    outs, counts = [], np.zeros(nb, dtype=np.int64)
+    for d in range(nb):
+        if only >= 0 and d != only:
+            continue
+        m = (b == d) | ((b == d + 1) & (dec < edges[d + 1] + halo)) | ((b == d - 1) & (dec >= edges[d] - halo))
+        idx = np.nonzero(m)[0]
+        bits = (row0 + idx).astype(np.uint64) | np.where(b[idx] == d, np.uint64(1 << 63), np.uint64(0))
+        outs.append(np.stack([ra[idx], dec[idx], bits.view(np.float64)], axis=1))
+        counts[d] = idx.size
+    out = np.concatenate(outs, axis=0) if outs else np.zeros((0, 3))
+    return torch.from_numpy(out.copy()), torch.from_numpy(counts)
+
+
+def _band_worker(rank, world, port, n1, n2, halo, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vif_b200 import catalogs as G
+    from vif_b200.distributed import qxmatch_banded, shard_bounds
+    from vif_b200.qxmatch import QxmatchParams
+    a1, b1 = G.fullsky(61, n1)
+    a2, b2 = G.fullsky(62, n2)
+    a2[:3] = a1[:3]; b2[:3] = b1[:3]                 # exact duplicates across the catalogs ...
+    a1[7] = a1[6]; b1[7] = b1[6]                      # ... and inside catalog 1 (reverse ties: smallest row)
+    lo, hi = shard_bounds(n1, world, rank)
+    ra2 = torch.from_numpy(a2.copy()) if rank == 0 else torch.zeros(n2, dtype=torch.float64)
+    dec2 = torch.from_numpy(b2.copy()) if rank == 0 else torch.zeros(n2, dtype=torch.float64)
+    ident, d, rev = qxmatch_banded(torch.from_numpy(a1[lo:hi].copy()), torch.from_numpy(b1[lo:hi].copy()), ra2, dec2, lo,
+                                   QxmatchParams(), halo_deg=halo, compute=_oracle_compute, partition=_np_partition,
+                                   bbox=_bbox)
+    _, _, full = qxmatch_banded(torch.from_numpy(a1[lo:hi].copy()), torch.from_numpy(b1[lo:hi].copy()), ra2, dec2, lo,
+                                QxmatchParams(), halo_deg=halo, gather_reverse=True, compute=_oracle_compute,
+                                partition=_np_partition, broadcast_cat2=False, bbox=_bbox)
+    fwd, _, _ = qxmatch_banded(torch.from_numpy(a1[lo:hi].copy()), torch.from_numpy(b1[lo:hi].copy()), ra2, dec2, lo,
+                               QxmatchParams(), halo_deg=halo, home=False, compute=_oracle_compute,
+                               partition=_np_partition, broadcast_cat2=False, bbox=_bbox)
+    k, k1 = rev["primary"].numpy(), fwd["primary"].numpy()
+    np.savez(os.path.join(out_dir, f"b{rank}.npz"), id=ident.numpy(), d=d.numpy(), rows=rev["rows"].numpy()[k],
+             rid=rev["rid"].numpy()[k], rd=rev["rd"].numpy()[k], rid_full=full["rid"].numpy(), rd_full=full["rd"].numpy(),
+             frows=fwd["rows"].numpy()[k1], fid=fwd["id"].numpy()[k1], fd=fwd["d"].numpy()[k1])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo", [(2, 8.0), (3, 8.0), (2, 0.05)], ids=["w2", "w3", "w2_fallback"])
+def test_banded_equals_single(tmp_path, oracle, world, halo):
+    """Forward rows come back to their owners, reverse rows stay with their band; both must equal the
+    single-process brute force (exact neighbours), duplicates included. halo = 0.05 deg is far too small
+    for 3000 sources on the sky: the completeness test must send the call to the row-sharded algorithm."""
+    from vif_b200 import catalogs as G
+    n1, n2 = 4000, 3000
+    port = _free_port()
+    mp.spawn(_band_worker, args=(world, port, n1, n2, halo, str(tmp_path)), nprocs=world, join=True)
+    a1, b1 = G.fullsky(61, n1)
+    a2, b2 = G.fullsky(62, n2)
+    a2[:3] = a1[:3]; b2[:3] = b1[:3]
+    a1[7] = a1[6]; b1[7] = b1[6]
+    exp = oracle.oracle_qxmatch(a1, b1, a2, b2, brute_force=True)
+    ids, ds, rows, frows = [], [], [], []
+    for r in range(world):
+        z = np.load(tmp_path / f"b{r}.npz")
+        ids.append(z["id"]); ds.append(z["d"]); rows.append(z["rows"])
+        assert np.array_equal(z["rid"].view(np.uint64), exp["rid"][z["rows"]])
+        assert np.array_equal(z["rd"], exp["rd"][z["rows"]])
+        assert np.array_equal(z["rid_full"].view(np.uint64), exp["rid"]) and np.array_equal(z["rd_full"], exp["rd"])
+        assert np.all(np.diff(z["rows"]) > 0)
+        # home=False: the forward results stay with the band, keyed by global row
+        assert np.array_equal(z["fid"].view(np.uint64), exp["id"][0][z["frows"]]) and np.array_equal(z["fd"], exp["d"][0][z["frows"]])
+        frows.append(z["frows"])
+    assert np.array_equal(np.concatenate(ids, axis=1).view(np.uint64), exp["id"])
+    assert np.array_equal(np.concatenate(ds, axis=1), exp["d"])
+    assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(n2))           # every catalog-2 row in exactly one band
+    assert np.array_equal(np.sort(np.concatenate(frows)), np.arange(n1))

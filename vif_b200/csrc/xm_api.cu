@@ -821,6 +821,37 @@ int32_t xm_release_memory(int32_t device) {
     return ok ? XM_OK : XM_ERR_CUDA;
 }
 
+int32_t xm_band_partition_dev(const double* ra, const double* dec, uint64_t n, uint64_t row0, const double* edges,
+                              int32_t nb, double halo, int32_t only, double* out, uint64_t cap, uint64_t* counts,
+                              uint64_t* total, int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    const bool bad = (n && (!ra || !dec)) || !edges || !counts || !total || (cap && !out) || n >= 0xfffffff0ull ||
+                     cap >= 0xfffffff0ull;
+    return dist_entry(device, stream, errbuf, errcap, bad, [&](Context*, cudaStream_t s, Error& err) -> int32_t {
+        Scratch scr;
+        XM_CUDA_TRY(scr.alloc(band_scratch_bytes(n, cap), s));
+        uint64_t launches = 0;
+        return launch_band_partition(ra, dec, (uint32_t)n, row0, edges, nb, halo, only, out, cap,
+                                     (unsigned long long*)counts, scr.p, total, s, err, &launches);
+    });
+}
+
+int32_t xm_band_finish_dev(int64_t* id_io, const double* d, const int64_t* bits_src, const int64_t* bits_cand, uint64_t n,
+                           double hlim, uint64_t* bad, int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    const bool badarg = (n && (!id_io || !d || !bits_src || !bits_cand)) || !bad || n >= 0xfffffff0ull;
+    return dist_entry(device, stream, errbuf, errcap, badarg, [&](Context*, cudaStream_t s, Error& err) {
+        return launch_band_finish((long long*)id_io, d, (const long long*)bits_src, (const long long*)bits_cand, (uint32_t)n,
+                                  hlim, (unsigned long long*)bad, s, err);
+    });
+}
+
+int32_t xm_band_home_dev(const double* got, const double* sent, uint64_t m, uint64_t row0, int64_t* id_out, double* d_out,
+                         int32_t device, void* stream, char* errbuf, uint64_t errcap) {
+    const bool badarg = (m && (!got || !sent || !id_out || !d_out)) || m >= 0xfffffff0ull;
+    return dist_entry(device, stream, errbuf, errcap, badarg, [&](Context*, cudaStream_t s, Error& err) {
+        return launch_band_home(got, (const long long*)sent, (uint32_t)m, row0, (long long*)id_out, d_out, s, err);
+    });
+}
+
 int32_t xm_fp64_peak(int32_t device, int32_t reps, double* tflops, char* errbuf, uint64_t errcap) {
     return dist_entry(device, nullptr, errbuf, errcap, !tflops,
                       [&](Context*, cudaStream_t s, Error& err) { return launch_fp64_peak(reps, tflops, s, err); });

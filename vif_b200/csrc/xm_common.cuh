@@ -89,6 +89,15 @@ size_t  qdist_scratch_bytes(uint64_t n);
 int32_t launch_qdist(const double* ra, const double* dec, uint64_t n, int model, void* scratch, double* out,
                      cudaStream_t s, Error& err);
 
+// xm_band.cu: order-preserving declination-band partition (multi-GPU exchange step)
+size_t  band_scratch_bytes(uint64_t n, uint64_t cap);
+int32_t launch_band_partition(const double* ra, const double* dec, uint32_t n, uint64_t row0, const double* edges,
+                              int nb, double halo, int only, double* out, uint64_t cap, unsigned long long* counts,
+                              void* scratch, uint64_t* total, cudaStream_t s, Error& err, uint64_t* launches);
+int32_t launch_band_finish(long long* id_io, const double* d, const long long* bits_src, const long long* bits_cand,
+                           uint32_t n, double hlim, unsigned long long* bad, cudaStream_t s, Error& err);
+int32_t launch_band_home(const double* got, const long long* sent, uint32_t m, uint64_t row0, long long* id_out,
+                         double* d_out, cudaStream_t s, Error& err);
 // xm_peak.cu
 int32_t launch_fp64_peak(int reps, double* tflops, cudaStream_t s, Error& err);
 

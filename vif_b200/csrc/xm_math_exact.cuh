@@ -78,24 +78,22 @@ __device__ __forceinline__ double true_to_proxy(double dist, bool linear, int mo
     return __dmul_rn(s, s);
 }
 
-// qxmatch.hpp:215-222
+// qxmatch.hpp:215-222: dist = 3600*(180/dpi)*2*asin(sqrt(p)).
+// For s = sqrt(p) < 0.01 (sources closer than ~1.1 deg: every binned match)
+// asin(s) = s(1 + s^2/6 + 3 s^4/40 + 15 s^6/336 + 105 s^8/3456 + ...), truncation error after the s^8 term
+// below 3e-22 relative -- 9 FP64 operations instead of the libm call, within 1 ulp of the correctly
+// rounded result (north-star tolerance on distances: 1e-9 relative). EVERY kernel converts through this
+// one function, so a distance does not depend on which kernel (filter or exact) decided its row.
 __device__ __forceinline__ double proxy_to_true(double p, bool linear) {
     if (linear) return __dsqrt_rn(p);
     const double k = __dmul_rn(__dmul_rn(3600.0, __ddiv_rn(180.0, XM_DPI)), 2.0);
-    return __dmul_rn(k, asin(__dsqrt_rn(p)));
-}
-
-// Same conversion for proxies of sources a few cells apart: s = sqrt(p) < 0.01, where
-// asin(s) = s(1 + s^2/6 + 3 s^4/40 + 15 s^6/336 + 105 s^8/3456 + ...) and the truncation error after
-// the s^8 term is below 3e-22 relative -- 9 FP64 operations instead of the libm call; the result
-// is within 1 ulp of the correctly rounded one (north-star tolerance on distances: 1e-9 relative).
-__device__ __forceinline__ double proxy_to_true_small(double p) {
-    const double k = __dmul_rn(__dmul_rn(3600.0, __ddiv_rn(180.0, XM_DPI)), 2.0);
     const double s = __dsqrt_rn(p);
     if (!(s < 0.01)) return __dmul_rn(k, asin(s));
-    const double t = fma(p, fma(p, fma(p, 105.0/3456.0, 15.0/336.0), 3.0/40.0), 1.0/6.0);
-    return __dmul_rn(k, fma(s*p, t, s));
+    const double t = __fma_rn(p, __fma_rn(p, __fma_rn(p, 105.0/3456.0, 15.0/336.0), 3.0/40.0), 1.0/6.0);
+    return __dmul_rn(k, __fma_rn(__dmul_rn(s, p), t, s));
 }
+
+__device__ __forceinline__ double proxy_to_true_small(double p) { return proxy_to_true(p, false); }
 
 // astro.hpp:33-39 (angdist, degrees -> arcsec) with the first point already converted:
 // x1r = d2r*ra1, y1r = d2r*dec1, c1 = cos(y1r).

@@ -79,10 +79,10 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     if params.self:
         raise ValueError("self-match shards catalog 1 against itself: pass the full catalog as "
                          "catalog 2 and self=False with an explicit id offset instead")
-    if broadcast_cat2 and world > 1:
-        dist.broadcast(ra2, src=src, group=group)
-        dist.broadcast(dec2, src=src, group=group)
-    mark("broadcast")
+    pending = []
+    if broadcast_cat2 and world > 1:          # in flight while the bounding box makes its two host round trips
+        pending = [dist.broadcast(ra2, src=src, group=group, async_op=True),
+                   dist.broadcast(dec2, src=src, group=group, async_op=True)]
 
     # global bounding box of catalog 1 (qxmatch.hpp:232-238): one all-reduce(max) on
     # (-ra_min, ra_max, -dec_min, dec_max)
@@ -91,7 +91,9 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     if world > 1:
         dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
     ext = ext.tolist()
-    mark("bbox")
+    for w in pending:
+        w.wait()
+    mark("broadcast+bbox")
     p = QxmatchParams(**{**params.__dict__, "bbox1": (-ext[0], ext[1], -ext[2], ext[3])})
 
     # the reverse results go straight into the peer-mapped exchange buffer of the merge when there is one
@@ -186,6 +188,280 @@ def qxmatch_partitioned(ra1_local, dec1_local, ra2, dec2, row_offset, n1_total, 
     p = QxmatchParams(**{**params.__dict__, "fwd_range": (int(row_offset), n_loc), "rev_range": (lo2, hi2 - lo2)})
     res = qxmatch(ra1, dec1, ra2, dec2, params=p)
     return res.id, res.d, res.rid, res.rd, (lo2, hi2)
+
+
+def band_edges(world, polar_weight=None):
+    """Declination bands [deg], equal in area except the two that hold a pole: the spherical search
+    hands the rows next to a pole to its exact kernel (xm_sphere.cu), about 9 ms of extra work per cap on
+    1e9 x 1e8, so those two bands get `polar_weight` (default 0.65 for 4 or more bands, else 1) of the
+    others' area. The outer edges are pushed past the poles so that every finite declination falls inside."""
+    import numpy as np
+    w = np.ones(world)
+    if world >= 4:
+        w[0] = w[-1] = 0.65 if polar_weight is None else float(polar_weight)
+    z = np.concatenate(([0.0], np.cumsum(w))) / w.sum()
+    e = np.degrees(np.arcsin(np.clip(-1.0 + 2.0 * z, -1.0, 1.0)))
+    e[0], e[-1] = -90.000001, 90.000001
+    return e
+
+
+def default_halo_deg(n1, n2):
+    """Halo width: six mean neighbour spacings of the sparser catalog (the chance that a nearest
+    neighbour lies further is exp(-36 pi)); rows that still fail the completeness test make the call
+    fall back to the row-sharded algorithm."""
+    import math
+    rho = max(min(n1, n2), 1) / (4.0 * math.pi)
+    return max(math.degrees(6.0 / math.sqrt(rho)), 1e-3)
+
+
+def _cuda_partition(ra, dec, row0, edges, halo, only):
+    """xm_band_partition_dev: (triples (m, 3) float64, counts (nb,) int64) -- see the ABI header."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    n, nb = ra.numel(), len(edges) - 1
+    # triples the output must hold: every row once, plus the rows within `halo` of an edge (estimated from
+    # the thinnest band with 50 % head room; a failed call is repeated with the safe bound of 3 per row)
+    thin = min(float(edges[k + 1] - edges[k]) for k in range(nb))
+    dup = min(2.0, 3.0 * float(halo) / max(thin, 1e-9)) if nb > 1 else 0.0
+    share = 1.0 if only < 0 else min(1.0, 3.0 / nb)
+    total = C.c_uint64()
+    err = C.create_string_buffer(512)
+    e = (C.c_double * (nb + 1))(*[float(v) for v in edges])
+    torch.cuda.current_stream(ra.device).synchronize()
+    for cap in (int(n * share * (1.0 + dup)) + 4096, 3 * n + 16):
+        cap = min(cap, 3 * n + 16)
+        out = torch.empty((cap, 3), dtype=torch.float64, device=ra.device)
+        counts = torch.zeros(nb, dtype=torch.int64, device=ra.device)
+        rc = lib.xm_band_partition_dev(ra.data_ptr(), dec.data_ptr(), n, int(row0), e, nb, float(halo), int(only),
+                                       out.data_ptr(), cap, counts.data_ptr(), C.byref(total), ra.device.index or 0, None,
+                                       err, 512)
+        if rc == 0:
+            break
+        if b"do not fit" not in err.value:
+            raise RuntimeError(err.value.decode())
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return out[:total.value], counts
+
+
+_ROW_MASK = 0x7FFFFFFFFFFFFFFF
+
+
+def _cuda_finish(idl, d, bits_src, bits_cand, hlim, bad):
+    """xm_band_finish_dev: candidate index -> global row in place, completeness count into `bad`."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    err = C.create_string_buffer(512)
+    torch.cuda.current_stream(idl.device).synchronize()
+    rc = _lib.load().xm_band_finish_dev(idl.data_ptr(), d.data_ptr(), bits_src.data_ptr(), bits_cand.data_ptr(), idl.numel(),
+                                        float(hlim), bad.data_ptr(), idl.device.index or 0, None, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+
+
+def _torch_finish(idl, d, bits_src, bits_cand, hlim, bad):
+    """Same contract with torch ops (CPU tensors: the gloo tests)."""
+    import torch
+    g = bits_cand & _ROW_MASK
+    idl.copy_(torch.where(idl >= 0, g[idl.clamp_min(0)], idl) if g.numel() else idl)
+    bad += ((bits_src < 0) & ~(d < hlim)).sum()
+
+
+def _cuda_home(got, sent, row_offset, id_out, d_out):
+    import ctypes as C
+    import torch
+    from . import _lib
+    err = C.create_string_buffer(512)
+    torch.cuda.current_stream(got.device).synchronize()
+    rc = _lib.load().xm_band_home_dev(got.data_ptr(), sent.data_ptr(), sent.shape[0], int(row_offset), id_out.data_ptr(),
+                                      d_out.data_ptr(), got.device.index or 0, None, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+
+
+def _torch_home(got, sent, row_offset, id_out, d_out):
+    import torch
+    sbits = sent[:, 2].contiguous().view(torch.int64)
+    own = torch.nonzero(sbits < 0).flatten()
+    rows = (sbits[own] & _ROW_MASK) - int(row_offset)
+    id_out[0, rows] = got[own, 0].contiguous().view(torch.int64)
+    d_out[0, rows] = got[own, 1]
+
+
+def qxmatch_banded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=None, src=0, broadcast_cat2=True,
+                   halo_deg=None, home=True, gather_reverse=False, compute=None, partition=None, bbox=None):
+    """Spatially decomposed multi-GPU qxmatch for catalogs too large to replicate (BASELINE config 5:
+    1e9 x 1e8 full sky): BOTH directions shard. The reference's threaded driver gives every worker a
+    chunk of catalog-1 rows and a chunk of catalog-2 rows over shared buckets (qxmatch.hpp:422-454);
+    across GPUs the buckets cannot be shared, so the rows are regrouped by declination band:
+
+      1. catalog 2 is replicated (NCCL broadcast from `src`, as the north star prescribes) while every
+         rank partitions its catalog-1 rows by band (xm_band_partition_dev: order preserving, rows
+         within `halo_deg` of an edge go to both sides);
+      2. the bands are exchanged with ONE NCCL all-to-all over NVLink (24 bytes per row: ra, dec, global
+         row) while rank b selects band b + halo out of catalog 2 (same kernel);
+      3. rank b runs the single-GPU search on band x band: the forward match of the band's catalog-1
+         rows and the reverse match of the band's catalog-2 rows each see every candidate closer than
+         the halo. The search has brute-force semantics (exact neighbours, equal proxies to the smallest
+         row; every band holds its rows in ascending global row order, so ties resolve as on one GPU);
+      4. completeness (xm_band_finish_dev): a result farther than the halo (or unmatched) could have a
+         nearer candidate outside the band. One all-reduce counts such rows; if there are any, the call
+         is redone by qxmatch_sharded (never observed on uniform catalogs: exp(-36 pi));
+      5. home=True: forward results travel back to the rows' owner ranks (second all-to-all, 16 bytes
+         per row) -> (id_local, d_local) as qxmatch_sharded returns them. home=False leaves them with
+         the band: fwd = dict(rows, primary, id, d) over the band's catalog-1 triples (rows = global row,
+         entries with primary == False are halo copies and carry no result of their own);
+         reverse results always stay with the band: rev = dict(rows, primary, rid, rd) (gather_reverse=True
+         assembles full-size replicated rid / rd instead).
+
+    Returns (id_local, d_local, rev) or, with home=False, (fwd, None, rev). nth = 1 only."""
+    import torch
+    import torch.distributed as dist
+    from .qxmatch import QxmatchParams
+
+    fallback_kw = {"compute": compute, "bbox": bbox}
+    on_gpu = ra1_local.is_cuda
+    compute = compute or _cuda_compute
+    partition = partition or _cuda_partition
+    finish = _cuda_finish if on_gpu else _torch_finish
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if params.nth > 1 or params.self or params.linear or params.no_mirror:
+        raise ValueError("qxmatch_banded serves nth = 1 spherical matches with the reverse match on")
+    timing = os.environ.get("XM_DIST_TIMING") and on_gpu
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
+    dev = ra1_local.device
+    n_loc, n2 = ra1_local.numel(), ra2.numel()
+    pending = []
+    if broadcast_cat2 and world > 1:          # in flight while catalog 1 is partitioned
+        pending = [dist.broadcast(ra2, src=src, group=group, async_op=True),
+                   dist.broadcast(dec2, src=src, group=group, async_op=True)]
+    edges = band_edges(world)
+    # catalog 1 holds about n_loc * world rows (contiguous row shards): no collective needed for the halo
+    halo = float(halo_deg) if halo_deg is not None else default_halo_deg(n_loc * world, n2)
+
+    # catalog 1: partition the local rows, exchange the bands
+    send1, cnt_send = partition(ra1_local, dec1_local, int(row_offset), edges, halo, -1)
+    cnt_recv = torch.empty_like(cnt_send)
+    if world > 1:
+        dist.all_to_all_single(cnt_recv, cnt_send, group=group)
+    else:
+        cnt_recv.copy_(cnt_send)
+    s_split, r_split = [int(v) for v in cnt_send.tolist()], [int(v) for v in cnt_recv.tolist()]
+    recv1 = torch.empty((sum(r_split), 3), dtype=torch.float64, device=dev)
+    for w in pending:
+        w.wait()
+    mark("partition+broadcast")
+    a2a = None
+    if world > 1:
+        a2a = dist.all_to_all_single(recv1, send1, r_split, s_split, group=group, async_op=True)
+    else:
+        recv1.copy_(send1)
+    # catalog 2: this rank's band + halo out of the replicated catalog (while the all-to-all is in flight)
+    sel2, _ = partition(ra2, dec2, 0, edges, halo, rank)
+    ra2b, dec2b = sel2[:, 0].contiguous(), sel2[:, 1].contiguous()
+    bits2 = sel2[:, 2].contiguous().view(torch.int64)
+    if a2a is not None:
+        a2a.wait()
+    ra1b, dec1b = recv1[:, 0].contiguous(), recv1[:, 1].contiguous()
+    bits1 = recv1[:, 2].contiguous().view(torch.int64)
+    mark("exchange+select")
+
+    # band x band with brute-force semantics through the exact spherical grid search: the exact nearest
+    # neighbours, i.e. what the reference's binned search returns wherever that search is exact
+    p = QxmatchParams(**{**params.__dict__, "bbox1": None, "brute_force": True, "exact_grid": True})
+    if ra1b.numel() and ra2b.numel():
+        res = compute(ra1b, dec1b, ra2b, dec2b, p)
+        idl, d = torch.as_tensor(res.id).view(torch.int64)[0], torch.as_tensor(res.d)[0]
+        ridl, rd = torch.as_tensor(res.rid).view(torch.int64), torch.as_tensor(res.rd)
+    else:                       # an empty band: nothing matched here, the completeness test decides
+        idl = torch.full((ra1b.numel(),), -1, dtype=torch.int64, device=dev)
+        d = torch.full((ra1b.numel(),), float("nan"), dtype=torch.float64, device=dev)
+        ridl = torch.full((ra2b.numel(),), -1, dtype=torch.int64, device=dev)
+        rd = torch.full((ra2b.numel(),), float("nan"), dtype=torch.float64, device=dev)
+    mark("compute")
+    # local candidate index -> global row; completeness
+    hlim = halo * 3600.0 * (1.0 - 1e-9)
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    finish(idl, d, bits1, bits2, hlim, bad)
+    finish(ridl, rd, bits2, bits1, hlim, bad)
+    if world > 1:
+        dist.all_reduce(bad, group=group)
+    if int(bad.item()) != 0:
+        if rank == 0 and os.environ.get("XM_DIST_TIMING"):
+            print("[qxmatch_banded] %d rows beyond the halo (%.4g deg): row-sharded fallback" % (int(bad.item()), halo), flush=True)
+        ident, dd, rid, rdd = qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, p, group=group, src=src,
+                                              broadcast_cat2=False, **fallback_kw)
+        if gather_reverse:
+            rev = {"rid": rid, "rd": rdd}
+        else:
+            rows = torch.nonzero((dec2 >= edges[rank]) & (dec2 < edges[rank + 1])).flatten()
+            rev = {"rows": rows, "primary": torch.ones_like(rows, dtype=torch.bool), "rid": rid[rows], "rd": rdd[rows]}
+        if home:
+            return ident, dd, rev
+        lo = int(row_offset)
+        rows1 = torch.arange(lo, lo + n_loc, device=dev)
+        return {"rows": rows1, "primary": torch.ones_like(rows1, dtype=torch.bool), "id": ident[0], "d": dd[0]}, None, rev
+    mark("complete")
+
+    rev = {"rows": bits2 & _ROW_MASK, "primary": bits2 < 0, "rid": ridl, "rd": rd}
+    if home:
+        # forward results back to the owners of the rows (same splits, other way round)
+        back = torch.stack((idl.view(torch.float64), d), dim=1)
+        got = torch.empty((send1.shape[0], 2), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_to_all_single(got, back, s_split, r_split, group=group)
+        else:
+            got.copy_(back)
+        id_local = torch.full((1, n_loc), -1, dtype=torch.int64, device=dev)
+        d_local = torch.full((1, n_loc), float("nan"), dtype=torch.float64, device=dev)
+        (_cuda_home if on_gpu else _torch_home)(got, send1, row_offset, id_local, d_local)
+        out = (id_local, d_local)
+        mark("home")
+    else:
+        out = ({"rows": bits1 & _ROW_MASK, "primary": bits1 < 0, "id": idl, "d": d}, None)
+
+    if gather_reverse:
+        keep2 = torch.nonzero(rev["primary"]).flatten()
+        rows2, rid2, rd2 = rev["rows"][keep2], rev["rid"][keep2], rev["rd"][keep2]
+        rid_full = torch.full((n2,), -1, dtype=torch.int64, device=dev)
+        rd_full = torch.full((n2,), float("nan"), dtype=torch.float64, device=dev)
+        if world > 1:
+            sizes = torch.tensor([keep2.numel()], dtype=torch.int64, device=dev)
+            allsz = [torch.empty_like(sizes) for _ in range(world)]
+            dist.all_gather(allsz, sizes, group=group)
+            mx = max(int(v.item()) for v in allsz)
+            pack = torch.zeros((mx, 3), dtype=torch.float64, device=dev)
+            pack[:keep2.numel(), 0] = rows2.view(torch.float64)
+            pack[:keep2.numel(), 1] = rid2.view(torch.float64)
+            pack[:keep2.numel(), 2] = rd2
+            allp = torch.empty((world * mx, 3), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allp, pack, group=group)
+            allp = allp.view(world, mx, 3)
+            for r in range(world):
+                m = int(allsz[r].item())
+                rr = allp[r, :m, 0].contiguous().view(torch.int64)
+                rid_full[rr] = allp[r, :m, 1].contiguous().view(torch.int64)
+                rd_full[rr] = allp[r, :m, 2]
+        else:
+            rid_full[rows2] = rid2
+            rd_full[rows2] = rd2
+        rev = {"rid": rid_full, "rd": rd_full}
+        mark("gather")
+    if timing and rank == 0:
+        print("[qxmatch_banded] halo=%.4g deg " % halo + " ".join("%s=%.3fms" % (marks[k][0], 1e3*(marks[k][1] - marks[k-1][1]))
+                                                                  for k in range(1, len(marks))), flush=True)
+    return out[0], out[1], rev
 
 
 _P2P = {}           # (device, n, world, group) -> symmetric buffers of the peer-memory merge
