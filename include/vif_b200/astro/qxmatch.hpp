@@ -22,6 +22,9 @@
 
 #include "vif/astro/astro.hpp"
 #include "vif_b200_qxmatch.h"
+// without cfitsio the reference has no vif::fits at all: the column-oriented tables of this path
+// (RA/DEC in, ID/D/RID/RD out, catalog_merge's cache files) are read and written by the shim
+#include "../io/colfits.hpp"
 
 #include <cstdint>
 #include <string>
@@ -41,8 +44,8 @@ namespace astro {
         MEMBERS2("qxmatch_res", MAKE_MEMBER(id), MAKE_MEMBER(d), MAKE_MEMBER(rid), MAKE_MEMBER(rd));
     };
 
-    #ifndef NO_CFITSIO
-    // same on-disk layout as the reference: one column-oriented table ID, D, RID, RD (qxmatch.hpp:19-29)
+    // same on-disk layout as the reference: one column-oriented table ID, D, RID, RD (qxmatch.hpp:19-29);
+    // through cfitsio where the reference was built with it, through io/colfits.hpp otherwise
     inline void qxmatch_save(const std::string& file, const qxmatch_res& r) {
         fits::write_table(file, ftable(r.id, r.d, r.rid, r.rd));
     }
@@ -52,7 +55,6 @@ namespace astro {
         fits::read_table(file, ftable(r.id, r.d, r.rid, r.rd));
         return r;
     }
-    #endif
 
     // field-for-field the reference's keyword set (qxmatch.hpp:31-39)
     struct qxmatch_params {
@@ -189,14 +191,12 @@ namespace astro {
         }
     }
 
-    #ifndef NO_CFITSIO
     inline void xmatch_save_lost(const id_pair& p, const std::string& save) {
         if (!p.lost.empty()) {
             warning(p.lost.size(), " sources failed to cross match");
             fits::write_table(save, ftable(p.lost));
         }
     }
-    #endif
 
     struct qdist_params {
         bool verbose = false;

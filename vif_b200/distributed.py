@@ -347,8 +347,15 @@ def qxmatch_banded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=N
         pending = [dist.broadcast(ra2, src=src, group=group, async_op=True),
                    dist.broadcast(dec2, src=src, group=group, async_op=True)]
     edges = band_edges(world)
-    # catalog 1 holds about n_loc * world rows (contiguous row shards): no collective needed for the halo
-    halo = float(halo_deg) if halo_deg is not None else default_halo_deg(n_loc * world, n2)
+    if halo_deg is not None:
+        halo = float(halo_deg)
+    else:
+        # every rank must use the SAME halo (senders duplicate rows by it, receivers test completeness
+        # against it): derive it from the largest shard, one 8-byte all-reduce
+        nmax = torch.tensor([n_loc], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+        halo = default_halo_deg(int(nmax.item()) * world, n2)
 
     # catalog 1: partition the local rows, exchange the bands
     send1, cnt_send = partition(ra1_local, dec1_local, int(row_offset), edges, halo, -1)
