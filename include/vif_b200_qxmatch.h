@@ -145,6 +145,17 @@ int32_t xm_band_finish_dev(int64_t* id_io, const double* d, const int64_t* bits_
 int32_t xm_band_home_dev(const double* got, const double* sent, uint64_t m, uint64_t row0, int64_t* id_out, double* d_out,
                          int32_t device, void* stream, char* errbuf, uint64_t errcap);
 
+/* The host libm's sin/cos decide the last bits of the reference's proxies (qxmatch.hpp:174-204); the
+ * library restates glibc 2.39's algorithm for them (csrc/xm_libm_glibc.cuh) and xm_init() checks the host
+ * libm against it. xm_libm_model: 1 = glibc's FMA build, 2 = its plain build, 0 = host libm not recognised
+ * (the device then uses the CUDA libm and near ties are only counted: xm_stats.rows_ambiguous). Needs no
+ * GPU. xm_libm_eval_host / _dev evaluate the restatement (which: 0 = sin, 1 = cos; |x| < 2.426, NaN
+ * beyond) on the host / on n device values, for tests. */
+int32_t xm_libm_model(void);
+double  xm_libm_eval_host(int32_t which, int32_t model, double x);
+int32_t xm_libm_eval_dev(int32_t which, int32_t model, const double* x, uint64_t n, double* out, int32_t device,
+                         void* stream, char* errbuf, uint64_t errcap);
+
 /* DFMA micro-benchmark: the FP64 roofline denominator of the brute-force path (BASELINE.md section 2:
  * "must be measured"). Runs `reps` launches of a kernel whose every thread carries 8 independent
  * chains of 4096 DFMAs (grid = 8 CTAs of 256 threads per SM), times them with CUDA events and

@@ -428,3 +428,26 @@ def test_random_differential(oracle):
         assert_same_result(got, exp, RTOL, f"case {case} {kind} n=({ra1.size},{ra2.size}) self={self_match} {kw}")
         seen.add((kind, kw["nth"] > 1, bool(kw.get("brute_force")), self_match))
     assert len(seen) > 25          # the draw did spread over the families
+
+
+# ---- partitioned runs (xm_params.has_ranges): block results must equal slices of the whole result ------
+@pytest.mark.parametrize("kw", [dict(), dict(nth=5), dict(self=True), dict(self=True, nth=5)],
+                         ids=["nth1", "nth5", "self_nth1", "self_nth5"])
+def test_row_ranges_equal_slices_of_the_unranged_result(kw):
+    """qxmatch.hpp:422-454 gives every thread a chunk of i and a chunk of j over shared buckets; has_ranges is that
+    split for one GPU of a partitioned multi-GPU run (outputs are block-local, ids global)."""
+    from vif_b200.qxmatch import QxmatchParams
+    n1, n2 = 120_000, 90_000
+    t1 = [torch.from_numpy(x).cuda() for x in G.c2(81, n1)]
+    t2 = t1 if kw.get("self") else [torch.from_numpy(x).cuda() for x in G.c2(82, n2)]
+    whole = qxmatch(*t1, *t2, **kw)
+    for fb, fc, rb, rc in ((0, 40_000, 0, 30_000), (40_000, 80_000, 30_000, 60_000), (119_999, 1, 89_999, 1), (5, 0, 7, 0)):
+        if kw.get("self"):
+            rb, rc = 0, 0                      # the binned self match has no reverse pass (qxmatch.hpp:395)
+        p = QxmatchParams(nth=kw.get("nth", 1), self=bool(kw.get("self")), no_mirror=bool(kw.get("self")),
+                          fwd_range=(fb, fc), rev_range=(rb, rc))
+        part = qxmatch(*t1, *t2, params=p)
+        assert torch.equal(part.id, whole.id[:, fb:fb + fc])
+        assert torch.equal(part.d.nan_to_num(-1.0), whole.d[:, fb:fb + fc].nan_to_num(-1.0))
+        if not kw.get("self"):
+            assert torch.equal(part.rid, whole.rid[rb:rb + rc]) and torch.equal(part.rd, whole.rd[rb:rb + rc])

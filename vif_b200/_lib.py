@@ -51,7 +51,7 @@ class XmStats(C.Structure):
 
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
-SYMBOLS = ["xm_band_partition_dev", "xm_band_finish_dev", "xm_band_home_dev", "xm_fp64_peak", "xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
+SYMBOLS = ["xm_libm_model", "xm_libm_eval_host", "xm_libm_eval_dev", "xm_band_partition_dev", "xm_band_finish_dev", "xm_band_home_dev", "xm_fp64_peak", "xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
            "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
@@ -93,6 +93,11 @@ def load():
                                        C.c_char_p, u64]
     lib.xm_band_home_dev.restype = i32
     lib.xm_band_home_dev.argtypes = [C.c_void_p, C.c_void_p, u64, u64, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_char_p, u64]
+    lib.xm_libm_model.restype = i32
+    lib.xm_libm_eval_host.restype = f64
+    lib.xm_libm_eval_host.argtypes = [i32, i32, f64]
+    lib.xm_libm_eval_dev.restype = i32
+    lib.xm_libm_eval_dev.argtypes = [i32, i32, C.c_void_p, u64, C.c_void_p, i32, C.c_void_p, C.c_char_p, u64]
     lib.xm_fp64_peak.restype = i32
     lib.xm_fp64_peak.argtypes = [i32, i32, C.POINTER(f64), C.c_char_p, u64]
     lib.xm_last_stats.restype = i32

@@ -237,7 +237,7 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
         if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
         rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
                                      g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint32_t>(), s, err,
-                                     launches);
+                                     launches, g.sin_model);
         if (rc) return rc;
     }
     out.view.rec = out.rec.as<Rec>(); out.view.cstart = out.cell.as<uint32_t>(); out.view.n = n;
@@ -326,6 +326,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
     const int sin_model = ctx->sin_model;
     memset(&st, 0, sizeof(st));
     st.sin_model = (uint64_t)sin_model;
+    st.cos_model = (uint64_t)sin_model;        // one libm model serves sin and cos (xm_libm_glibc.cuh)
     uint64_t launches = 0;
     int32_t rc;
 
@@ -400,12 +401,12 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         Scratch x1, y1, c1, x2, y2, c2;
         XM_CUDA_TRY(x1.alloc(n1*8, s)); XM_CUDA_TRY(y1.alloc(n1*8, s)); XM_CUDA_TRY(c1.alloc(n1*8, s));
         if ((rc = launch_prep_unsorted(ra1, dec1, (uint32_t)n1, linear, x1.as<double>(), y1.as<double>(),
-                                       c1.as<double>(), s, err, &launches))) return rc;
+                                       c1.as<double>(), s, err, &launches, sin_model))) return rc;
         const double *px2 = x1.as<double>(), *py2 = y1.as<double>(), *pc2 = c1.as<double>();
         if (!same_cat) {
             XM_CUDA_TRY(x2.alloc(n2*8, s)); XM_CUDA_TRY(y2.alloc(n2*8, s)); XM_CUDA_TRY(c2.alloc(n2*8, s));
             if ((rc = launch_prep_unsorted(ra2, dec2, (uint32_t)n2, linear, x2.as<double>(),
-                                           y2.as<double>(), c2.as<double>(), s, err, &launches))) return rc;
+                                           y2.as<double>(), c2.as<double>(), s, err, &launches, sin_model))) return rc;
             px2 = x2.as<double>(); py2 = y2.as<double>(); pc2 = c2.as<double>();
         }
         const bool fast = !P.exact_only && brute_fast_applicable(linear, (uint32_t)nth);
@@ -734,8 +735,9 @@ int32_t check_args(const double* ra1, const double* dec1, uint64_t n1, const dou
                    uint64_t* rid, double* rd, Error& err) {
     if ((n1 && (!ra1 || !dec1)) || (n2 && (!ra2 || !dec2)))
         return fail(err, XM_ERR_INVALID_ARG, "NULL coordinate pointer");
-    if (n1 && (!id || !d)) return fail(err, XM_ERR_INVALID_ARG, "NULL id/d output pointer");
-    if (!p->no_mirror && n2 && (!rid || !rd))
+    const uint64_t n1o = p->has_ranges ? p->fwd_count : n1, n2o = p->has_ranges ? p->rev_count : n2;   // rows the outputs cover
+    if (n1o && (!id || !d)) return fail(err, XM_ERR_INVALID_ARG, "NULL id/d output pointer");
+    if (!p->no_mirror && n2o && (!rid || !rd))
         return fail(err, XM_ERR_INVALID_ARG, "NULL rid/rd output pointer while no_mirror is false");
     return XM_OK;
 }
@@ -849,6 +851,18 @@ int32_t xm_band_home_dev(const double* got, const double* sent, uint64_t m, uint
     const bool badarg = (m && (!got || !sent || !id_out || !d_out)) || m >= 0xfffffff0ull;
     return dist_entry(device, stream, errbuf, errcap, badarg, [&](Context*, cudaStream_t s, Error& err) {
         return launch_band_home(got, (const long long*)sent, (uint32_t)m, row0, (long long*)id_out, d_out, s, err);
+    });
+}
+
+int32_t xm_libm_model(void) { return calibrate_sin_model(); }
+
+double xm_libm_eval_host(int32_t which, int32_t model, double x) { return libm_host_eval(which, model, x); }
+
+int32_t xm_libm_eval_dev(int32_t which, int32_t model, const double* x, uint64_t n, double* out, int32_t device,
+                         void* stream, char* errbuf, uint64_t errcap) {
+    const bool bad = (n && (!x || !out)) || model < 1 || model > 2 || which < 0 || which > 1;
+    return dist_entry(device, stream, errbuf, errcap, bad, [&](Context*, cudaStream_t s, Error& err) {
+        return launch_libm_eval(which, model, x, n, out, s, err);
     });
 }
 

@@ -16,6 +16,7 @@
 // Cells holding more than kMaxCellSort rows are left unordered and reported through *overflow; the
 // caller then rebuilds that catalog with the stable radix sort (xm_sort.cu), which has no such limit.
 #include "xm_common.cuh"
+#include "xm_math_exact.cuh"
 
 namespace xm {
 
@@ -144,7 +145,7 @@ place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint
         if (i >= n) continue;
         double x, y, c;
         if (g.linear) { x = r[k]; y = d[k]; c = 1.0; }
-        else { y = __dmul_rn(d[k], XM_D2R); x = __dmul_rn(r[k], XM_D2R); c = cos(y); }   // qxmatch.hpp:174-180
+        else { y = __dmul_rn(d[k], XM_D2R); x = __dmul_rn(r[k], XM_D2R); c = cos_ref(y, g.sin_model); }   // qxmatch.hpp:174-180
         const unsigned long long w = (unsigned long long)i | ((unsigned long long)key[k] << 32);
         asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(out + slot[k]), "l"(__double_as_longlong(x)),
                      "l"(__double_as_longlong(y)), "l"(__double_as_longlong(c)), "l"(w) : "memory");

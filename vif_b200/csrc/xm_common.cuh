@@ -74,7 +74,8 @@ int32_t fail(Error& err, int32_t code, const char* fmt, ...);
 // ---- host geometry (xm_geometry.cpp) ------------------------------------------------------
 void grid_from_bbox(const double* bb1, const double* bb2, uint64_t n2, uint64_t nth, bool linear,
                     xm_grid* g);
-int  calibrate_sin_model();   // probes the host libm: 1 = FMA Taylor model, 2 = non-FMA
+int  calibrate_sin_model();   // probes the host libm: 1 = glibc 2.39 FMA build, 2 = plain build, 0 = not recognised
+double libm_host_eval(int which, int model, double x);   // host side of the restatement (0 = sin, 1 = cos)
 
 // ---- launchers -----------------------------------------------------------------------------
 // xm_index.cu
@@ -98,6 +99,7 @@ int32_t launch_band_finish(long long* id_io, const double* d, const long long* b
                            uint32_t n, double hlim, unsigned long long* bad, cudaStream_t s, Error& err);
 int32_t launch_band_home(const double* got, const long long* sent, uint32_t m, uint64_t row0, long long* id_out,
                          double* d_out, cudaStream_t s, Error& err);
+int32_t launch_libm_eval(int which, int model, const double* x, uint64_t n, double* out, cudaStream_t s, Error& err);
 // xm_peak.cu
 int32_t launch_fp64_peak(int reps, double* tflops, cudaStream_t s, Error& err);
 
@@ -118,7 +120,7 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
                                 Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
-                                uint64_t* launches);
+                                uint64_t* launches, int model);
 // xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
 size_t  bucket_scan_aux_bytes(uint32_t ncell);
 void    launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches);
@@ -202,7 +204,7 @@ int32_t launch_sphere_search(const GridView& g, int wrap, const double* cmin_row
                              cudaEvent_t ev_join, Error& err, uint64_t* launches);
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
-                             uint64_t* launches);
+                             uint64_t* launches, int model);
 int32_t launch_fill_outputs(uint64_t* id, double* d, uint64_t n, double dval, cudaStream_t s,
                             Error& err, uint64_t* launches);
 

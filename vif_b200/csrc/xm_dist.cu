@@ -20,7 +20,7 @@ __device__ __forceinline__ double angdist_deg(double tra1, double tdec1, double 
     const double sra = sin_ref(__dmul_rn(0.5, __dsub_rn(ra2, ra1)), model);
     const double sde = sin_ref(__dmul_rn(0.5, __dsub_rn(dec2, dec1)), model);
     const double h = __dadd_rn(__dmul_rn(sde, sde),
-                               __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cos(dec2)), cos(dec1)));
+                               __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cos_ref(dec2, model)), cos_ref(dec1, model)));
     return __ddiv_rn(__dmul_rn(__dmul_rn(3600.0, 2.0), asin(__dsqrt_rn(h))), d2r);
 }
 
@@ -43,20 +43,30 @@ angdist_less_kernel(const double* __restrict__ tra1, const double* __restrict__ 
     const double ra1 = __dmul_rn(d2r, tra1[i]), dec1 = __dmul_rn(d2r, tdec1[i]);
     const double sra = sin_ref(__dmul_rn(0.5, __dsub_rn(ra2, ra1)), model);
     const double sde = sin_ref(__dmul_rn(0.5, __dsub_rn(dec2, dec1)), model);
-    const double p = __dadd_rn(__dmul_rn(sde, sde), __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cdec2), cos(dec1)));
+    const double p = __dadd_rn(__dmul_rn(sde, sde), __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cdec2), cos_ref(dec1, model)));
     out[i] = p < crad ? 1 : 0;
+}
+
+// test hook: the device side of the glibc restatement
+__global__ void __launch_bounds__(256)
+libm_eval_kernel(int which, int model, const double* __restrict__ x, uint64_t n, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    const bool ok = which == 0 ? glibc::sin_small(model, x[i], &r) : glibc::cos_small(model, x[i], &r);
+    out[i] = ok ? r : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // qxmatch.hpp:690-693
 __global__ void __launch_bounds__(256)
 qdist_prep_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint64_t n,
-                  double* __restrict__ x, double* __restrict__ y, double* __restrict__ c) {
+                  int model, double* __restrict__ x, double* __restrict__ y, double* __restrict__ c) {
     const uint64_t i = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double d2r = XM_D2R;
     x[i] = __dmul_rn(ra[i], d2r);
     y[i] = __dmul_rn(dec[i], d2r);
-    c[i] = cos(y[i]);
+    c[i] = cos_ref(y[i], model);
 }
 
 // row j of the matrix per blockIdx.y (grid-stride), columns i along threads: coalesced row stores
@@ -106,9 +116,16 @@ int32_t launch_qdist(const double* ra, const double* dec, uint64_t n, int model,
     double* y = x + n;
     double* c = y + n;
     const unsigned bx = (unsigned)((n + 255)/256);
-    qdist_prep_kernel<<<bx, 256, 0, s>>>(ra, dec, n, x, y, c);
+    qdist_prep_kernel<<<bx, 256, 0, s>>>(ra, dec, n, model, x, y, c);
     const dim3 grid(bx, (unsigned)(n < 32768 ? n : 32768));
     qdist_kernel<<<grid, 256, 0, s>>>(x, y, c, n, model, out);
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
+int32_t launch_libm_eval(int which, int model, const double* x, uint64_t n, double* out, cudaStream_t s, Error& err) {
+    if (n == 0) return XM_OK;
+    libm_eval_kernel<<<(unsigned)((n + 255)/256), 256, 0, s>>>(which, model, x, n, out);
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
 }

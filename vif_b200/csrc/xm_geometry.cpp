@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "xm_common.cuh"
+#include "xm_libm_glibc.cuh"
 
 namespace xm {
 
@@ -99,28 +100,46 @@ void grid_from_bbox(const double* bb1, const double* bb2, uint64_t n2, uint64_t 
     g->nc2 = nc2; g->area = area;
 }
 
-// Which build of glibc's Taylor branch does this host's sin() follow? (see xm_math_exact.cuh)
+// Which build of glibc 2.39's sin/cos does this host's libm follow? 1: the -mfma build (contracted
+// a*b+c), 2: the plain build, 0: neither (another libm or glibc version) -- then the device uses the
+// CUDA libm and near ties are only counted (xm_stats.rows_ambiguous). Every probe must agree: the
+// arguments cover the Taylor branch of sin, both table branches and the pi/2 - |x| branches of both.
 int calibrate_sin_model() {
     static const double probes[] = {
         0x1.e4d7129b19786p-4, -0x1.9a74be59977e6p-5, 0x1.73d97b094ef53p-4, 0x1.d1a8d18d90886p-4,
         -0x1.f649c97d63135p-4, 0x1.9e46618447c9dp-4, -0x1.e72bb4939298ap-4, 0x1.c677bc6a3ec59p-4,
-        0x1.b1c4f64361285p-4, 0x1.dbe65e5e43c19p-4, -0x1.b8a4933f18125p-4, -0x1.d2cddbf963a44p-4};
-    const double s1 = -0x1.5555555555555p-3, s2 = 0x1.1111111110ECEp-7, s3 = -0x1.A01A019DB08B8p-13,
-                 s4 = 0x1.71DE27B9A7ED9p-19, s5 = -0x1.ADDFFC2FCDF59p-26;
-    int hit_fma = 0, hit_plain = 0;
-    for (double x : probes) {
-        volatile double vx = x;                 // keep the libm call
-        const double ref = std::sin(vx);
-        const double xx = x*x;
-        const double pf = std::fma(std::fma(std::fma(std::fma(s5, xx, s4), xx, s3), xx, s2), xx, s1);
-        volatile double a = s5*xx; a = a + s4; a = a*xx; a = a + s3; a = a*xx; a = a + s2;
-        a = a*xx; a = a + s1;
-        volatile double tf = pf*x; tf = tf*xx;
-        volatile double tp = a*x;  tp = tp*xx;
-        if (ref == x + tf) ++hit_fma;
-        if (ref == x + tp) ++hit_plain;
+        0x1.b1c4f64361285p-4, 0x1.dbe65e5e43c19p-4, -0x1.b8a4933f18125p-4, -0x1.d2cddbf963a44p-4,
+        1e-9, 3.3e-5, -0.0021, 0.0871557427, 0.13, -0.2617993878, 0.3141592, 0.5, -0.61, 0.7853981634, 0.85,
+        0.86, -0.9, 1.0, 1.0471975512, -1.2, 1.3962634016, 1.5, 1.5707963267948966, -1.5707, 1.7, 2.0, -2.3, 2.42};
+    bool ok[3] = {false, true, true};
+    unsigned seed = 12345u;
+    for (int it = 0; it < 4096; ++it) {
+        double x;
+        if (it < (int)(sizeof(probes)/sizeof(probes[0]))) x = probes[it];
+        else {                                   // pseudo-random arguments in (-2.42, 2.42), denser near 0
+            seed = seed*1664525u + 1013904223u;
+            const double u = (double)(seed >> 8)/16777216.0;
+            seed = seed*1664525u + 1013904223u;
+            const double v = (double)(seed >> 8)/16777216.0;
+            x = (2.0*u - 1.0)*2.42*(it % 3 == 0 ? v*v : 1.0);
+        }
+        volatile double vx = x;                  // keep the libm calls
+        const double rs = std::sin(vx), rc = std::cos(vx);
+        for (int m = 1; m <= 2; ++m) {
+            double es = 0.0, ec = 0.0;
+            if (!glibc::sin_small(m, x, &es) || !glibc::cos_small(m, x, &ec) || es != rs || ec != rc) ok[m] = false;
+        }
     }
-    return hit_plain > hit_fma ? 2 : 1;
+    if (ok[1]) return 1;
+    if (ok[2]) return 2;
+    return 0;
+}
+
+double libm_host_eval(int which, int model, double x) {
+    double r = NAN;
+    if (which == 0) { if (!glibc::sin_small(model, x, &r)) r = NAN; }
+    else if (!glibc::cos_small(model, x, &r)) r = NAN;
+    return r;
 }
 
 }  // namespace xm

@@ -5,6 +5,7 @@
 // (:146-149), the unit conversion (:170-181) and the vector-of-vectors bucket fill (:270-288).
 // All of it is HBM-bound streaming work: coalesced loads, one pass per array.
 #include "xm_common.cuh"
+#include "xm_math_exact.cuh"
 
 namespace xm {
 
@@ -90,7 +91,7 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
 __global__ void __launch_bounds__(kThreads)
 cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
                     const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
-                    int linear, Rec* __restrict__ rec) {
+                    int linear, int model, Rec* __restrict__ rec) {
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t i = perm[p];
@@ -102,7 +103,7 @@ cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restri
     } else {
         out.y = __dmul_rn(d, XM_D2R);
         out.x = __dmul_rn(r, XM_D2R);
-        out.c = cos(out.y);
+        out.c = cos_ref(out.y, model);
     }
     rec[p] = out;
 }
@@ -235,10 +236,10 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
                                 Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
-                                uint64_t* launches) {
+                                uint64_t* launches, int model) {
     cell_offsets_kernel<<<(ncell + 1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, n, ncell, cstart);
     cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
-                                                                        linear ? 1 : 0, rec);
+                                                                        linear ? 1 : 0, model, rec);
     *launches += 2;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;

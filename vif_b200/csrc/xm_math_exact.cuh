@@ -14,6 +14,7 @@
 // (GridView::sin_model). Outside that range the CUDA libm sin (<= 2 ulp) is used.
 #pragma once
 #include "xm_common.cuh"
+#include "xm_libm_glibc.cuh"
 
 namespace xm {
 
@@ -33,16 +34,30 @@ __device__ __forceinline__ double sin_taylor_glibc(double x, int model) {
 }
 
 __device__ __forceinline__ double sin_ref(double x, int model) {
+    if (model == 0) return sin(x);          // host libm not recognised (xm_init): CUDA libm, <= 2 ulp
     const double ax = fabs(x);
     if (ax < 0.126) {
         if (ax < 0x1p-26) return x;
         return sin_taylor_glibc(x, model);
     }
+    // 0.126 <= |x| < 2.426: glibc's table branches restated (xm_libm_glibc.cuh); beyond: CUDA libm (<= 2 ulp)
+    double r;
+    if (glibc::sin_small(model, x, &r)) return r;
     return sin(x);
+}
+
+// cos(dec) of a catalog row as the host libm computes it (qxmatch.hpp:176,180). model = the libm model
+// xm_init() recognised (1 FMA build, 2 plain build of glibc 2.39); 0 = not recognised: CUDA libm, and the
+// exact kernels' ambiguity counter (xm_stats.rows_ambiguous) stays the only guard.
+__device__ __forceinline__ double cos_ref(double x, int model) {
+    double r;
+    if (model != 0 && glibc::cos_small(model, x, &r)) return r;
+    return cos(x);
 }
 
 // same, for callers that guarantee |x| < 0.126 (coordinates a few cells apart): no libm fallback
 __device__ __forceinline__ double sin_ref_small(double x, int model) {
+    if (model == 0) return sin(x);
     if (fabs(x) < 0x1p-26) return x;
     return sin_taylor_glibc(x, model);
 }
@@ -104,7 +119,7 @@ __device__ __forceinline__ double angdist_pre(double x1r, double y1r, double c1,
     const double sra = sin_ref(__dmul_rn(0.5, __dsub_rn(ra2, x1r)), model);
     const double sde = sin_ref(__dmul_rn(0.5, __dsub_rn(dec2, y1r)), model);
     const double h = __dadd_rn(__dmul_rn(sde, sde),
-                               __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cos(dec2)), c1));
+                               __dmul_rn(__dmul_rn(__dmul_rn(sra, sra), cos_ref(dec2, model)), c1));
     return __ddiv_rn(__dmul_rn(__dmul_rn(3600.0, 2.0), asin(__dsqrt_rn(h))), d2r);
 }
 

@@ -445,13 +445,13 @@ brute_exact_kernel(int sin_model, const double* __restrict__ x1, const double* _
 }
 
 __global__ void prep_unsorted_kernel(const double* __restrict__ ra, const double* __restrict__ dec,
-                                     uint32_t n, int linear, double* __restrict__ x,
+                                     uint32_t n, int linear, int model, double* __restrict__ x,
                                      double* __restrict__ y, double* __restrict__ c) {
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double r = ra[i], d = dec[i];
     if (linear) { x[i] = r; y[i] = d; c[i] = 1.0; }
-    else { const double yr = __dmul_rn(d, XM_D2R); x[i] = __dmul_rn(r, XM_D2R); y[i] = yr; c[i] = cos(yr); }
+    else { const double yr = __dmul_rn(d, XM_D2R); x[i] = __dmul_rn(r, XM_D2R); y[i] = yr; c[i] = cos_ref(yr, model); }
 }
 
 __global__ void fill_outputs_kernel(uint64_t* __restrict__ id, double* __restrict__ d, uint64_t n,
@@ -564,9 +564,9 @@ int32_t launch_brute_exact(const GridView& g, const double* x1, const double* y1
 
 int32_t launch_prep_unsorted(const double* ra, const double* dec, uint32_t n, bool linear,
                              double* x, double* y, double* c, cudaStream_t s, Error& err,
-                             uint64_t* launches) {
+                             uint64_t* launches, int model) {
     if (n == 0) return XM_OK;
-    prep_unsorted_kernel<<<(n + 255)/256, 256, 0, s>>>(ra, dec, n, linear ? 1 : 0, x, y, c);
+    prep_unsorted_kernel<<<(n + 255)/256, 256, 0, s>>>(ra, dec, n, linear ? 1 : 0, model, x, y, c);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;

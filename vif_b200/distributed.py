@@ -37,6 +37,10 @@ def _cuda_bbox(ra, dec):
     bad = C.c_uint64()
     err = C.create_string_buffer(512)
     import torch
+    if ra.numel() == 0:
+        # an empty row shard (fewer rows than ranks): neutral element of the min/max all-reduce, so that the
+        # rank still enters every collective of the call
+        return [float("inf"), float("-inf"), float("inf"), float("-inf")]
     torch.cuda.current_stream(ra.device).synchronize()
     rc = lib.xm_bbox_dev(ra.data_ptr(), dec.data_ptr(), ra.numel(), ra.device.index or 0, None, out,
                          C.byref(bad), err, 512)
