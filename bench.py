@@ -371,10 +371,72 @@ def run_gpu_arm(args):
     else:
         e2e_value, e2e_steps, h2d, d2h, dt = run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params,
                                                      dev, barrier, qxmatch, qxmatch_sharded)
+    # ---- BASELINE config 5 (1e9 x 1e8 full sky) beside the headline line: strong scaling over the same N ----
+    args.c5_strong = None
+    if args.config == "c2" and n1 == N_FULL * (world if args.scaling == "weak" else 1) and not os.environ.get("XM_BENCH_NO_C5"):
+        del ra1, dec1, ra2, dec2, out
+        args.c5_strong = run_c5_strong(world, rank, local, dev, barrier)
     if rank == 0:
         emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_acc, e2e_value, e2e_steps, h2d, d2h, dt)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c5_strong(world, rank, local, dev, barrier, n1=1_000_000_000, n2=100_000_000, steps=3):
+    """C5 at its full size on the N GPUs of this run: one GPU answers the binned call with the exact spherical
+    search; N > 1 regroup catalog 1 into declination bands (qxmatch_banded: both directions sharded, results stay
+    with the band). Device-resident inputs, CUDA-event time of `steps` calls after 2 warm-ups, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from vif_b200 import catalogs as G, _lib
+    from vif_b200 import qxmatch
+    from vif_b200.qxmatch import QxmatchParams
+    from vif_b200.distributed import qxmatch_banded, shard_bounds
+    try:
+        _lib.load().xm_release_memory(-1)
+        torch.cuda.empty_cache()
+        lo, hi = shard_bounds(n1, world, rank)
+        need = (hi - lo) * 125 + n2 * 110                    # inputs, results, index and search scratch [bytes]
+        ok = torch.tensor([1 if torch.cuda.mem_get_info(dev)[0] > need else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)         # every rank takes the same decision
+        if int(ok.item()) == 0:
+            return {"skipped": "needs %.0f GB of free HBM per GPU" % (need / 1e9)}
+        ra1, dec1 = gen_catalog(G, "c5", 1, hi - lo, dev, start=lo)
+        if rank == 0:
+            ra2, dec2 = gen_catalog(G, "c5", 2, n2, dev)
+        else:
+            ra2 = torch.empty(n2, dtype=torch.float64, device=dev)
+            dec2 = torch.empty(n2, dtype=torch.float64, device=dev)
+        params = QxmatchParams(device=local)
+
+        def step():
+            if world == 1:
+                return qxmatch(ra1, dec1, ra2, dec2, params=params)
+            return qxmatch_banded(ra1, dec1, ra2, dec2, lo, params, home=False)
+        for _ in range(2):
+            keep = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            keep = step()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        del keep, ra1, dec1, ra2, dec2
+        _lib.load().xm_release_memory(-1)
+        torch.cuda.empty_cache()
+        return {"workload": workload_desc(n1, n2, "c5"), "n_gpus": world, "steps": steps, "ms_per_step": ms.item(),
+                "value": n1 / (ms.item() * 1e-3), "unit": UNIT, "scaling": "strong",
+                "bytes": 16 * n1 + 16 * n2 + 16 * n1 + 16 * n2,
+                "hbm_GBps_whole_path": (16 * n1 + 16 * n2 + 16 * n1 + 16 * n2) / (ms.item() * 1e-3) / 1e9,
+                "parallelism": ("1 rank" if world == 1 else
+                                "declination bands, one NCCL all-to-all of catalog 1, results stay with the band")}
+    except Exception as e:          # noqa: BLE001 -- the headline line must not depend on this extra
+        return {"error": (str(e).splitlines() or ["?"])[0][:300]}
 
 
 def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev, barrier, qxmatch, qxmatch_sharded):

@@ -451,3 +451,31 @@ def test_row_ranges_equal_slices_of_the_unranged_result(kw):
         assert torch.equal(part.d.nan_to_num(-1.0), whole.d[:, fb:fb + fc].nan_to_num(-1.0))
         if not kw.get("self"):
             assert torch.equal(part.rid, whole.rid[rb:rb + rc]) and torch.equal(part.rd, whole.rd[rb:rb + rc])
+
+
+# ---- the FP64 filter kernel against its numpy model (tests/ring_filter_model.py) ----------------------------
+@pytest.mark.parametrize("name", ["c1_box", "tall_dec_field", "high_dec_box", "displaced_copies", "large_cells", "self"])
+def test_fp64_filter_flags_the_rows_its_model_flags(oracle, name, monkeypatch):
+    """the model restates ring_nn_filter_kernel's decision logic; the kernel must hand the
+    same number of rows to the exact kernel (xm_stats.rows_refined_fwd). The kernel contracts a*b+c where numpy
+    rounds twice, so a row sitting within an ulp of one of the thresholds may fall either way: the counts must
+    agree to max(2, 1 %)."""
+    import sys
+    sys.path.insert(0, HERE)
+    from ring_filter_model import run_filter
+    from test_ring_filter_model import CASES as MODEL_CASES
+    c1, c2, self_match = MODEL_CASES[name]()
+    if c2 is None:
+        c2 = c1
+    bb1 = (c1[0].min(), c1[0].max(), c1[1].min(), c1[1].max())
+    bb2 = (c2[0].min(), c2[0].max(), c2[1].min(), c2[1].max())
+    grid = oracle.oracle_grid(bb1, bb2, c2[0].size)
+    acc, win, _ = run_filter(c1[0], c1[1], c2[0], c2[1], grid, self_match)
+    monkeypatch.setenv("XM_FILTER", "v1")
+    got = qxmatch(c1[0], c1[1], None if self_match else c2[0], None if self_match else c2[1], no_mirror=True)
+    flagged_model = int((~acc).sum())
+    flagged_kernel = int(got.stats["rows_refined_fwd"])
+    print("\n[%s] model flags %d rows, kernel %d of %d" % (name, flagged_model, flagged_kernel, acc.size))
+    assert abs(flagged_kernel - flagged_model) <= max(2, flagged_model // 100)
+    exp = oracle.oracle_qxmatch(c1[0], c1[1], c2[0], c2[1], self=self_match, thread=8, no_mirror=True)
+    assert np.array_equal(got.id, exp["id"])
