@@ -568,6 +568,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         }
         // ---- forward search (lane s) ----
         bool timed_f = false, timed_r = false;
+        int tile_f = 0;
         Scratch refine, resrec, plans;
         if (srcF->n == 0) {
             // empty block: nothing to match
@@ -582,6 +583,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
                                            &launches, ctx->kev[0], ctx->kev[1]))) return rc;
                 timed_f = true;
+                tile_f = tile;
             } else {
                 XM_CUDA_TRY(plans.alloc(filter_plan_bytes(n1o), s));
                 if ((rc = launch_ring_nn_filter(g, *srcF, *v2, self, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
@@ -626,7 +628,8 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                         XM_CUDA_TRY(plans2.alloc(nn32_plan_bytes(n2o, g.nra, tile), s2));
                         if ((rc = launch_ring_nn32(g, *srcR, s1.view, false, tile, rid, rd, resrec2.p, plans2.p,
                                                    refine2.as<uint32_t>(), &ctx->d_ctr->refine_rev, true, ctx->d_ctr,
-                                                   s2, ctx->lane_ev[2], err, &launches, ctx->kev[2], ctx->kev[3]))) return rc;
+                                                   s2, ctx->lane_ev[2], err, &launches, ctx->kev[2], ctx->kev[3],
+                                                   (timed_f && tile_f == tile && !getenv("XM_NN32_CONCURRENT")) ? ctx->kev[1] : nullptr))) return rc;
                         timed_r = true;
                     } else {
                         XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));

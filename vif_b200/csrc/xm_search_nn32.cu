@@ -441,6 +441,295 @@ ring_nn32_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __rest
     if (lane == 0 && evals) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, (unsigned long long)evals);
 }
 
+// ---- persistent, warp-specialised form (tiles of kCons = 192 sources) ------------------------------------------
+// ncu on the kernel above (profiles/r2_nn32_kernel_ncu.txt): a third of the stall samples sit on the two
+// dependent global-memory latencies at the head of every CTA (plan -> records) and another fifth on the
+// barriers behind them; occupancy is register-bound (5 CTAs of 192), so more warps cannot hide them.
+// Here a CTA lives for the whole launch and walks tiles blockIdx, blockIdx + grid, ...:
+//   * 2 PRODUCER warps fetch tile t+1 (plan, candidate runs, source records, CSR offsets, row table),
+//     convert it to the FP32 tile frame and fill the other of two shared-memory stages;
+//   * 6 CONSUMER warps (one thread per source) run rings 0 and 1 on the current stage;
+//   * full / empty hand-over through named barriers (bar.arrive / bar.sync), consumer-only barriers
+//     for the pooling steps. The consumers never wait for global memory except for the winner's
+//     record in the epilogue (their own record is requested when the tile starts and used at the end).
+#ifndef XM_NN32_CONS
+#define XM_NN32_CONS 192
+#endif
+constexpr int kCons = XM_NN32_CONS, kProd = 256 - kCons, kPThreads = kCons + kProd;
+#ifndef XM_NN32_PB
+#define XM_NN32_PB 4
+#endif
+constexpr int kPB = XM_NN32_PB;        // candidate records a producer thread keeps in flight
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;          // named barriers: full[2] = 1,2; empty[2] = 3,4
+
+struct __align__(16) Stage32 {
+    float4   c[kCap];                    // candidates {U, V, G, -}
+    float4   a[kCons];                   // sources {us, vsk, ks, ry}
+    float4   b[kCons];                   // sources {vs, c1f, gs, -}
+    uint4    plan[3];
+    uint32_t cs[3][kRowsMax + 1];
+    float    ccen[kRowsMax + 1];
+};
+
+struct __align__(16) Persist32 {
+    Stage32  st[2];
+    uint32_t item[kCons*kQ];
+    int2     part[kCons*kQ];
+    uint32_t wtot[kCons/32];
+};
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+template <bool SELF>
+__global__ void __launch_bounds__(kPThreads, 4)
+ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __restrict__ plan,
+                  const uint32_t* __restrict__ ntiles_dev, ResRec* __restrict__ res,
+                  uint32_t* __restrict__ refine_list, unsigned long long* refine_count, int reverse,
+                  SearchCounters* ctr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Persist32& sm = *reinterpret_cast<Persist32*>(smem_raw);
+    const uint32_t ntiles = *ntiles_dev;
+    const int tid = threadIdx.x;
+    const float wxf = __double2float_rn(g.wx), wyf = __double2float_rn(g.wy);
+
+    if (tid >= kCons) {
+        // ================================ producers ================================
+        // The plan of the next tile is requested while the current one is staged; a tile's own loads go out in
+        // batches of four 32-byte records per thread (deeper batches spill: measured slower).
+        const int pt = tid - kCons;
+        int buf = 0;
+        const uint4* pp0 = reinterpret_cast<const uint4*>(plan + blockIdx.x);
+        uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa;
+        if (blockIdx.x < ntiles) { pa = __ldg(pp0); pb = __ldg(pp0 + 1); pc = __ldg(pp0 + 2); }
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, buf ^= 1) {
+            Stage32& S = sm.st[buf];
+            const uint4 qa = pa, qb = pb, qc = pc;
+            if (t + gridDim.x < ntiles) {
+                const uint4* pn = reinterpret_cast<const uint4*>(plan + t + gridDim.x);
+                pa = __ldg(pn); pb = __ldg(pn + 1); pc = __ldg(pn + 2);
+            }
+            const uint32_t p0 = qa.x, cnt = qa.y;
+            const uint32_t rs0 = qa.z, rs1 = qa.w, rs2 = qb.x, rc0 = qb.y, rc1 = qb.z, rc2 = qb.w;
+            const int ya = (int)qc.x;
+            const uint32_t xs = qc.y;
+            const int nrows = (int)qc.z;
+            bar_sync(kBarEmpty + buf, kPThreads);                    // the consumers are done with this stage
+            if (pt < 3) S.plan[pt] = pt == 0 ? qa : (pt == 1 ? qb : qc);
+            if (nrows > 0) {
+                const double X0 = g.ox + ((double)xs + 0.5)*g.wx;
+                const double Y0 = g.oy + ((double)ya + 0.5*(double)nrows)*g.wy;
+                const uint32_t tot = rc0 + rc1 + rc2;
+                uint32_t csv[3] = {0u, 0u, 0u};
+                double ccv = 0.0;
+                if (pt <= nrows) {
+#pragma unroll
+                    for (int col = 0; col < 3; ++col) {
+                        const int cx = (int)xs - 1 + col;
+                        if (cx >= 0 && cx < (int)g.nra) csv[col] = __ldg(cand.cstart + (uint32_t)cx*g.ndec + (uint32_t)(ya + pt));
+                    }
+                    if (pt < nrows) ccv = __ldg(g.ccen_row + ya + pt);
+                }
+                // the tile's sources: raw record -> frame parameters
+                for (uint32_t k = pt; k < cnt; k += kProd) {
+                    const Rec me = load_rec(src.rec + p0 + k);
+                    const float us = __double2float_rn(me.x - X0), vs = __double2float_rn(me.y - Y0);
+                    const float c1f = __double2float_rn(me.c);
+                    const float gs = sqrt_apx(c1f);
+                    const float ks = rcp_apx(gs);
+                    const int ry = (int)(me.key - xs*g.ndec) - ya;
+                    S.a[k] = make_float4(us, vs*ks, ks, __int_as_float(ry));
+                    S.b[k] = make_float4(vs, c1f, gs, 0.0f);
+                }
+                for (uint32_t base = 0; base < tot; base += (uint32_t)(kPB*kProd)) {
+                    Rec r[kPB];
+#pragma unroll
+                    for (int k = 0; k < kPB; ++k) {
+                        const uint32_t q = base + (uint32_t)(k*kProd + pt);
+                        r[k].x = r[k].y = 0.0; r[k].c = 1.0;
+                        if (q < tot) {
+                            const uint32_t gi = q < rc0 ? rs0 + q : (q < rc0 + rc1 ? rs1 + (q - rc0) : rs2 + (q - rc0 - rc1));
+                            r[k] = load_rec(cand.rec + gi);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kPB; ++k) {
+                        const uint32_t q = base + (uint32_t)(k*kProd + pt);
+                        if (q < tot) {
+                            const float u = __double2float_rn(r[k].x - X0), v = __double2float_rn(r[k].y - Y0);
+                            const float G = sqrt_apx(__double2float_rn(r[k].c));
+                            S.c[q] = make_float4(u*G, v, G, 0.0f);
+                        }
+                    }
+                }
+                if (pt <= nrows) {
+                    S.cs[0][pt] = csv[0]; S.cs[1][pt] = csv[1]; S.cs[2][pt] = csv[2];
+                    if (pt < nrows) S.ccen[pt] = __double2float_rn(ccv);
+                }
+            }
+            bar_arrive(kBarFull + buf, kPThreads);
+        }
+        return;
+    }
+
+    // ================================ consumers ================================
+    const int lane = tid & 31, wid = tid >> 5;
+    bar_arrive(kBarEmpty + 0, kPThreads);
+    bar_arrive(kBarEmpty + 1, kPThreads);
+    const float eps_lo = __double2float_ru(g.eps_lo), eps_hi = __double2float_ru(g.eps_hi);
+    const float eps = eps_lo + eps_hi + 0x1p-20f;
+    const float csr = __double2float_rn(g.cs_rad);
+    uint32_t evals = 0;
+    int buf = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, buf ^= 1) {
+        Stage32& S = sm.st[buf];
+        bar_sync(kBarFull + buf, kPThreads);
+        const uint4 pa = S.plan[0], pb = S.plan[1], pc = S.plan[2];
+        const uint32_t p0 = pa.x, cnt = pa.y;
+        const uint32_t rs0 = pa.z, rs1 = pa.w, rs2 = pb.x, rc0 = pb.y, rc1 = pb.z;
+        const int nrows = (int)pc.z;
+        const float cminT = __uint_as_float(pc.w);
+        const bool live = (uint32_t)tid < cnt;
+        const uint32_t p = p0 + tid;
+        Rec me;
+        me.x = me.y = me.c = 0.0; me.idx = 0; me.key = 0;
+        if (live) me = load_rec(src.rec + p);                     // used in the epilogue only
+        if (nrows == 0) {                                          // neighbourhood too large for the stage
+            bar_arrive(kBarEmpty + buf, kPThreads);
+            if (live) {
+                const unsigned long long pos = atomicAdd(refine_count, 1ull);
+                refine_list[pos] = p;
+                store_res(res + me.idx, kUndecidedId, 0.0);
+            }
+            continue;
+        }
+        const uint32_t d0 = 0u - rs0, d1 = rc0 - rs1, d2 = rc0 + rc1 - rs2;
+        const float4 A = S.a[live ? tid : 0], B = S.b[live ? tid : 0];
+        const float us = A.x, vsk = A.y, ks = A.z, vs = B.x, c1f = B.y, gs = B.z;
+        const int ry = __float_as_int(A.w);
+        const float ymax = 0.5f*(float)nrows*wyf*(1.0f + 0x1p-20f) + __double2float_ru(g.fzy);
+        const float eband = fmaf(ks, 0x1p-23f*(20.0f*wyf + 3.0f*ymax), 0x1p-19f*wxf)*(1.0f + 0x1p-10f);
+
+        // ---- ring 0 ----
+        int32_t h1 = kInfF, h2 = kInfF;
+        const uint32_t self_li = SELF ? p + d1 : 0xffffffffu;
+        bool flag = false, done = !live;
+        uint32_t mask = 0;
+        float cd = 0.0f, sdelta = 0.0f;
+        if (live) {
+            const uint32_t qs = S.cs[1][ry] + d1, qe = S.cs[1][ry + 1] + d1;
+            scan32<SELF>(S.c, qs, qe, us, vsk, ks, self_li, h1, h2);
+            evals += qe - qs;
+            const float ylo = ((float)ry - 0.5f*(float)nrows)*wyf;
+            const float dyc = vs - (ylo + 0.5f*wyf);
+            cd = sqrt_apx(fmaf(us*us*S.ccen[ry], c1f, dyc*dyc));
+            sdelta = __double2float_ru(g.stop_delta) + 1.2f*(0x1p-22f*(wxf + 2.0f*ymax) + 0x1p-19f*cd) + 0x1p-20f*csr;
+            const float hi1 = dist_hi(h1, eband), lo1 = dist_lo(h1, eband);
+            {
+                const float dhi = h1 >= kInfF ? __int_as_float(kInfF) : hi1*gs*(1.0f + 0x1p-20f);
+                const float dlo = h1 >= kInfF ? __int_as_float(kInfF) : lo1*gs*(1.0f - 0x1p-20f);
+                const int dec = stop_decision32(dlo, dhi, 0.4f*csr - 1.1f*cd, sdelta, eps_lo, eps_hi);
+                if (dec == 0) done = true; else if (dec == 2) { flag = true; done = true; }
+            }
+            if (!done) {
+                const float mx = __double2float_ru(g.fzx) + 0x1p-22f*wxf, my = __double2float_ru(g.fzy) + 0x1p-22f*ymax;
+                const float hwx = 0.5f*wxf;
+                const float sc = sqrt_apx(cminT)*(1.0f - 0x1p-20f);
+                const float ksl = ks*(1.0f - 0x1p-19f);
+                const float xl = fmaxf((us + hwx) - mx, 0.0f)*sc, xr = fmaxf((hwx - us) - mx, 0.0f)*sc;
+                const float yd = fmaxf((vs - ylo) - my, 0.0f)*ksl, yu = fmaxf(((ylo + wyf) - vs) - my, 0.0f)*ksl;
+                const float T = (h1 >= kInfF) ? __int_as_float(kInfF) : hi1*hi1*(1.0f + 2.0f*eps + 0x1p-18f);
+                const float xl2 = xl*xl, xr2 = xr*xr, yd2 = yd*yd, yu2 = yu*yu;
+                mask = (yu2 < T ? 1u : 0u) | (xr2 < T ? 2u : 0u) | (yd2 < T ? 4u : 0u) | (xl2 < T ? 8u : 0u) |
+                       (xr2 + yu2 < T ? 16u : 0u) | (xl2 + yu2 < T ? 32u : 0u) | (xl2 + yd2 < T ? 64u : 0u) |
+                       (xr2 + yd2 < T ? 128u : 0u);
+                if (ry + 1 >= nrows) mask &= ~(1u | 16u | 32u);
+                if (ry - 1 < 0) mask &= ~(4u | 64u | 128u);
+                const float wxs = wxf*(1.0f - 0x1p-20f)*sc, wys = wyf*(1.0f - 0x1p-20f)*ksl;
+                const float o = fminf(fminf((xl + wxs)*(xl + wxs), (xr + wxs)*(xr + wxs)),
+                                      fminf((yd + wys)*(yd + wys), (yu + wys)*(yu + wys)));
+                if (!(o >= T) || __popc(mask) > kQ) { flag = true; done = true; mask = 0; }
+            }
+        }
+
+        // ---- pool the surviving (source, cell) pairs (consumer-only barriers) ----
+        const uint32_t nq = __popc(mask);
+        uint32_t inc = nq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) sm.wtot[wid] = inc;
+        bar_sync(kBarCons, kCons);
+        uint32_t first = inc - nq, total = 0;
+#pragma unroll
+        for (int k = 0; k < kCons/32; ++k) {
+            const uint32_t w = sm.wtot[k];
+            if (k < wid) first += w;
+            total += w;
+        }
+        {
+            uint32_t m = mask, k = first;
+            while (m) {
+                const uint32_t e = __ffs(m) - 1;
+                m &= m - 1;
+                sm.item[k++] = (uint32_t)tid | (e << 8);
+            }
+        }
+        bar_sync(kBarCons, kCons);
+        for (uint32_t it = tid; it < total; it += kCons) {
+            const uint32_t item = sm.item[it];
+            const uint32_t owner = item & 0xffu, e = item >> 8;
+            const int bx = (int)((0x20020121u >> (4*e)) & 3u) - 1;
+            const int by = (int)((0x00221012u >> (4*e)) & 3u) - 1;
+            const float4 o = S.a[owner];
+            const int r = __float_as_int(o.w) + by;
+            const uint32_t dd = bx < 0 ? d0 : (bx > 0 ? d2 : d1);
+            const uint32_t qs = S.cs[bx + 1][r] + dd, qe = S.cs[bx + 1][r + 1] + dd;
+            int32_t a1 = kInfF, a2 = kInfF;
+            scan32<false>(S.c, qs, qe, o.x, o.y, o.z, 0xffffffffu, a1, a2);
+            evals += qe - qs;
+            sm.part[it] = make_int2(a1, a2);
+        }
+        bar_sync(kBarCons, kCons);
+        bar_arrive(kBarEmpty + buf, kPThreads);                    // the stage may be refilled from here on
+        for (uint32_t k = 0; k < nq; ++k) {
+            const int2 a = sm.part[first + k];
+            h2 = min(min(h2, a.y), max(h1, a.x));
+            h1 = min(h1, a.x);
+        }
+
+        // ---- decide ----
+        if (live) {
+            const float hi1 = dist_hi(h1, eband);
+            if (h1 >= kInfF) flag = true;
+            if (!done && !flag) {
+                const float lo1 = dist_lo(h1, eband);
+                const int dec = stop_decision32(lo1*gs*(1.0f - 0x1p-20f), hi1*gs*(1.0f + 0x1p-20f), 2.4f*csr - 1.1f*cd,
+                                                sdelta, eps_lo, eps_hi);
+                if (dec != 0) flag = true;
+            }
+            if (!flag && h2 < kInfF && !(hi1*(1.0f + eps) < dist_lo(h2, eband))) flag = true;
+            if (flag) {
+                const unsigned long long pos = atomicAdd(refine_count, 1ull);
+                refine_list[pos] = p;
+                store_res(res + me.idx, kUndecidedId, 0.0);
+            } else {
+                const uint32_t li = (uint32_t)(h1 & kIdxMask);
+                const uint32_t slot = li < rc0 ? rs0 + li : (li < rc0 + rc1 ? rs1 + (li - rc0) : rs2 + (li - rc0 - rc1));
+                const Rec w = load_rec(cand.rec + slot);
+                const double pr = proxy_sph_small(me.x, me.y, me.c, w.x, w.y, w.c, g.sin_model);
+                store_res(res + me.idx, (uint64_t)w.idx, proxy_to_true_small(pr));
+            }
+        }
+        // the merge above read sm.part of this tile: the next tile's pooling must not overwrite it earlier
+        bar_sync(kBarCons, kCons);
+    }
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
+    if (lane == 0 && evals) atomicAdd(reverse ? &ctr->evals_rev : &ctr->evals_fwd, (unsigned long long)evals);
+}
+
 }  // namespace
 
 // Sources per tile for catalogs of n_src / n_cand rows on grid g, 0 when the FP32 kernel does not apply:
@@ -474,7 +763,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
                          uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                          uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                          SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
-                         uint64_t* launches, cudaEvent_t k0, cudaEvent_t k1) {
+                         uint64_t* launches, cudaEvent_t k0, cudaEvent_t k1, cudaEvent_t after) {
     if (src.n == 0) return XM_OK;
     const uint32_t ntiles = src.n/(uint32_t)tile + g.nra + 1;
     TilePlan32* plan = (TilePlan32*)plan_scratch;
@@ -485,6 +774,31 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
     *launches += 1;
     launch_exclusive_scan_u32(toff, g.nra + 1, aux, s, launches);
     plan_tiles32_kernel<<<(ntiles + 255)/256, 256, 0, s>>>(g, src, cand, toff, (uint32_t)tile, ntiles, plan);
+    const char* pe = getenv("XM_NN32_PERSIST");
+    if (tile == kCons && !(pe && pe[0] == '0')) {
+        // persistent, warp-specialised form: 4 CTAs per SM for the whole launch
+        int dev = 0, sms = 148;
+        XM_CUDA_TRY(cudaGetDevice(&dev));
+        XM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const uint32_t grid = (uint32_t)sms*4u < ntiles ? (uint32_t)sms*4u : ntiles;
+        if (self) XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn32p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Persist32)));
+        else XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn32p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Persist32)));
+        // `after`: the other direction's persistent launch, which fills every SM on its own -- running the two one
+        // after the other costs nothing and lets the first lane's results leave for the host early
+        if (after) XM_CUDA_TRY(cudaStreamWaitEvent(s, after, 0));
+        if (k0) XM_CUDA_TRY(cudaEventRecord(k0, s));
+        if (self) ring_nn32p_kernel<true><<<grid, kPThreads, sizeof(Persist32), s>>>(g, src, cand, plan, toff + g.nra, res, refine_list,
+                                                                                      refine_count, reverse ? 1 : 0, ctr);
+        else ring_nn32p_kernel<false><<<grid, kPThreads, sizeof(Persist32), s>>>(g, src, cand, plan, toff + g.nra, res, refine_list,
+                                                                                  refine_count, reverse ? 1 : 0, ctr);
+        *launches += 2;
+        if (k1) XM_CUDA_TRY(cudaEventRecord(k1, s));
+        if (filter_done) XM_CUDA_TRY(cudaEventRecord(filter_done, s));
+        int32_t rcp = launch_unpack_results(result_scratch, src.n, id_out, d_out, s, err, launches);
+        if (rcp) return rcp;
+        XM_CUDA_TRY(cudaGetLastError());
+        return XM_OK;
+    }
     // prefetch distance: about one wave of resident CTAs (XM_NN32_AHEAD overrides; 0 switches it off)
     uint32_t ahead = 148u*4u;
     if (const char* e = getenv("XM_NN32_AHEAD")) ahead = (uint32_t)atoi(e);
