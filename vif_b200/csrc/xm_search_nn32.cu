@@ -184,6 +184,57 @@ __device__ __forceinline__ int stop_decision32(float d_lo, float d_hi, float tr,
     return 2;
 }
 
+// What remains to be done for a source after ring 0 (its own cell), given the smallest tracked value h1.
+//   * mask: the neighbour cells (bit e as in the pooling step) that can hold a candidate nearer than, or within
+//     the error band of, the best so far. Gaps to the own cell's edges in the tile frame, shrunk by the rounding
+//     of the frame coordinates and of the binning (fzx, fzy).
+//   * mask == 0 (and the 16 outer cells of the 5x5 block out of reach as well): nothing the reference visits
+//     later, however deep it goes, can replace or tie the best so far (qxmatch.hpp:318 is a strict <), so the
+//     row is decided without looking at the stop rule.
+//   * mask != 0: the reference's stop rule after ring 0 (qxmatch.hpp:336-340, max_dist = cs/2) says whether it
+//     looks at those cells at all; certain stop -> decided, certain continue -> scan them, else flag.
+//     No stop rule is needed after ring 1: depth 1 of the reference is the whole 5x5 block and whatever it
+//     visits beyond the masked cells is out of reach by the bounds above.
+// Returns the mask; flag: the exact kernel must decide the row.
+__device__ __forceinline__ uint32_t ring0_decide(int32_t h1, float us, float vs, float ks, float gs, float c1f,
+                                                 float ccen, int ry, int nrows, float cminT, float wxf, float wyf,
+                                                 float ymax, float eband, float eps, float eps_lo, float eps_hi,
+                                                 float csr, float fzx, float fzy, float stop_delta, bool& flag) {
+    const float hi1 = dist_hi(h1, eband);
+    const float ylo = ((float)ry - 0.5f*(float)nrows)*wyf;               // lower edge of the own cell row
+    const float mx = fzx + 0x1p-22f*wxf, my = fzy + 0x1p-22f*ymax;
+    const float hwx = 0.5f*wxf;
+    const float sc = sqrt_apx(cminT)*(1.0f - 0x1p-20f);
+    const float ksl = ks*(1.0f - 0x1p-19f);
+    const float xl = fmaxf((us + hwx) - mx, 0.0f)*sc, xr = fmaxf((hwx - us) - mx, 0.0f)*sc;
+    const float yd = fmaxf((vs - ylo) - my, 0.0f)*ksl, yu = fmaxf(((ylo + wyf) - vs) - my, 0.0f)*ksl;
+    const float T = (h1 >= kInfF) ? __int_as_float(kInfF) : hi1*hi1*(1.0f + 2.0f*eps + 0x1p-18f);
+    const float xl2 = xl*xl, xr2 = xr*xr, yd2 = yd*yd, yu2 = yu*yu;
+    uint32_t mask = (yu2 < T ? 1u : 0u) | (xr2 < T ? 2u : 0u) | (yd2 < T ? 4u : 0u) | (xl2 < T ? 8u : 0u) |
+                    (xr2 + yu2 < T ? 16u : 0u) | (xl2 + yu2 < T ? 32u : 0u) | (xl2 + yd2 < T ? 64u : 0u) |
+                    (xr2 + yd2 < T ? 128u : 0u);
+    // rows outside the grid do not exist (qxmatch.hpp:309-311); columns outside it are empty runs
+    if (ry + 1 >= nrows) mask &= ~(1u | 16u | 32u);
+    if (ry - 1 < 0) mask &= ~(4u | 64u | 128u);
+    // the 16 outer cells of the 5x5 block lie a full cell further
+    const float wxs = wxf*(1.0f - 0x1p-20f)*sc, wys = wyf*(1.0f - 0x1p-20f)*ksl;
+    const float o = fminf(fminf((xl + wxs)*(xl + wxs), (xr + wxs)*(xr + wxs)),
+                          fminf((yd + wys)*(yd + wys), (yu + wys)*(yu + wys)));
+    if (!(o >= T) || __popc(mask) > kQ) { flag = true; return 0u; }
+    if (mask == 0u) return 0u;
+    // distance to the cell centre (small-angle form of qxmatch.hpp:298-299)
+    const float dyc = vs - (ylo + 0.5f*wyf);
+    const float cd = sqrt_apx(fmaf(us*us*ccen, c1f, dyc*dyc));
+    // slack of the ring radius: the FP64 filter's (small-angle forms) + the FP32 evaluation of cd
+    const float sdelta = stop_delta + 1.2f*(0x1p-22f*(wxf + 2.0f*ymax) + 0x1p-19f*cd) + 0x1p-20f*csr;
+    const float lo1 = dist_lo(h1, eband);
+    const int dec = stop_decision32(lo1*gs*(1.0f - 0x1p-20f), hi1*gs*(1.0f + 0x1p-20f), 0.4f*csr - 1.1f*cd, sdelta,
+                                    eps_lo, eps_hi);
+    if (dec == 0) return 0u;                     // the reference stops after ring 0: the best so far is its answer
+    if (dec == 2) { flag = true; return 0u; }
+    return mask;
+}
+
 template <bool SELF>
 __global__ void __launch_bounds__(kMaxT, XM_NN32_MINB)
 ring_nn32_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __restrict__ plan,
@@ -297,50 +348,15 @@ ring_nn32_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __rest
     int32_t h1 = kInfF, h2 = kInfF;
     const uint32_t self_li = SELF ? p + d1 : 0xffffffffu;
     uint32_t evals = 0;
-    bool flag = false, done = !live;
+    bool flag = false;
     uint32_t mask = 0;
-    float cd = 0.0f, sdelta = 0.0f;
     if (live) {
         const uint32_t qs = s_cs[1][ry] + d1, qe = s_cs[1][ry + 1] + d1;
         scan32<SELF>(s_c, qs, qe, us, vsk, ks, self_li, h1, h2);
         evals += qe - qs;
-        // distance to the cell centre (small-angle form of qxmatch.hpp:298-299) and the stop rule after
-        // ring 0 (max_dist = cs/2, qxmatch.hpp:336-340)
-        const float ylo = ((float)ry - 0.5f*(float)nrows)*wyf;               // lower edge of the own cell row
-        const float dyc = vs - (ylo + 0.5f*wyf);
-        cd = sqrt_apx(fmaf(us*us*s_ccen[ry], c1f, dyc*dyc));
-        // slack of the ring radius: the FP64 filter's (small-angle forms) + the FP32 evaluation of cd
-        sdelta = __double2float_ru(g.stop_delta) + 1.2f*(0x1p-22f*(wxf + 2.0f*ymax) + 0x1p-19f*cd) + 0x1p-20f*csr;
-        const float hi1 = dist_hi(h1, eband), lo1 = dist_lo(h1, eband);
-        {
-            const float dhi = h1 >= kInfF ? __int_as_float(kInfF) : hi1*gs*(1.0f + 0x1p-20f);
-            const float dlo = h1 >= kInfF ? __int_as_float(kInfF) : lo1*gs*(1.0f - 0x1p-20f);
-            const int dec = stop_decision32(dlo, dhi, 0.4f*csr - 1.1f*cd, sdelta, eps_lo, eps_hi);
-            if (dec == 0) done = true; else if (dec == 2) { flag = true; done = true; }
-        }
-        if (!done) {
-            // ---- which of the 8 neighbours can hold a winner (or a near tie)? Gaps to the own cell's edges,
-            // shrunk by the rounding of the frame coordinates and of the binning (fzx, fzy).
-            const float mx = __double2float_ru(g.fzx) + 0x1p-22f*wxf, my = __double2float_ru(g.fzy) + 0x1p-22f*ymax;
-            const float hwx = 0.5f*wxf;
-            const float sc = sqrt_apx(cminT)*(1.0f - 0x1p-20f);
-            const float ksl = ks*(1.0f - 0x1p-19f);
-            const float xl = fmaxf((us + hwx) - mx, 0.0f)*sc, xr = fmaxf((hwx - us) - mx, 0.0f)*sc;
-            const float yd = fmaxf((vs - ylo) - my, 0.0f)*ksl, yu = fmaxf(((ylo + wyf) - vs) - my, 0.0f)*ksl;
-            const float T = (h1 >= kInfF) ? __int_as_float(kInfF) : hi1*hi1*(1.0f + 2.0f*eps + 0x1p-18f);
-            const float xl2 = xl*xl, xr2 = xr*xr, yd2 = yd*yd, yu2 = yu*yu;
-            mask = (yu2 < T ? 1u : 0u) | (xr2 < T ? 2u : 0u) | (yd2 < T ? 4u : 0u) | (xl2 < T ? 8u : 0u) |
-                   (xr2 + yu2 < T ? 16u : 0u) | (xl2 + yu2 < T ? 32u : 0u) | (xl2 + yd2 < T ? 64u : 0u) |
-                   (xr2 + yd2 < T ? 128u : 0u);
-            // rows outside the grid do not exist (qxmatch.hpp:309-311); columns outside it are empty runs
-            if (ry + 1 >= nrows) mask &= ~(1u | 16u | 32u);
-            if (ry - 1 < 0) mask &= ~(4u | 64u | 128u);
-            // the 16 outer cells of the 5x5 block lie a full cell further
-            const float wxs = wxf*(1.0f - 0x1p-20f)*sc, wys = wyf*(1.0f - 0x1p-20f)*ksl;
-            const float o = fminf(fminf((xl + wxs)*(xl + wxs), (xr + wxs)*(xr + wxs)),
-                                  fminf((yd + wys)*(yd + wys), (yu + wys)*(yu + wys)));
-            if (!(o >= T) || __popc(mask) > kQ) { flag = true; done = true; mask = 0; }
-        }
+        mask = ring0_decide(h1, us, vs, ks, gs, c1f, s_ccen[ry], ry, nrows, cminT, wxf, wyf, ymax, eband, eps, eps_lo,
+                            eps_hi, csr, __double2float_ru(g.fzx), __double2float_ru(g.fzy),
+                            __double2float_ru(g.stop_delta), flag);
     }
 
     // ---- 2. pool the surviving (source, cell) pairs ------------------------------------------------------
@@ -414,13 +430,6 @@ ring_nn32_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __rest
     if (live) {
         const float hi1 = dist_hi(h1, eband);
         if (h1 >= kInfF) flag = true;
-        if (!done && !flag) {
-            // stop rule after ring 1 (max_dist = 2.5 cs): going on to ring 2 is the exact kernel's job
-            const float lo1 = dist_lo(h1, eband);
-            const int dec = stop_decision32(lo1*gs*(1.0f - 0x1p-20f), hi1*gs*(1.0f + 0x1p-20f), 2.4f*csr - 1.1f*cd,
-                                            sdelta, eps_lo, eps_hi);
-            if (dec != 0) flag = true;
-        }
         // the winner must beat the runner-up by more than the band
         if (!flag && h2 < kInfF && !(hi1*(1.0f + eps) < dist_lo(h2, eband))) flag = true;
 
@@ -460,6 +469,7 @@ constexpr int kCons = XM_NN32_CONS, kProd = 256 - kCons, kPThreads = kCons + kPr
 #define XM_NN32_PB 4
 #endif
 constexpr int kPB = XM_NN32_PB;        // candidate records a producer thread keeps in flight
+constexpr int kSrcPer = (kCons + kProd - 1)/kProd;    // source records per producer thread
 constexpr int kBarFull = 1, kBarEmpty = 3, kBarCons = 5;          // named barriers: full[2] = 1,2; empty[2] = 3,4
 
 struct __align__(16) Stage32 {
@@ -481,7 +491,7 @@ struct __align__(16) Persist32 {
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 
-template <bool SELF>
+template <bool SELF, bool PF>
 __global__ void __launch_bounds__(kPThreads, 4)
 ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __restrict__ plan,
                   const uint32_t* __restrict__ ntiles_dev, ResRec* __restrict__ res,
@@ -530,16 +540,30 @@ ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __res
                     }
                     if (pt < nrows) ccv = __ldg(g.ccen_row + ya + pt);
                 }
-                // the tile's sources: raw record -> frame parameters
-                for (uint32_t k = pt; k < cnt; k += kProd) {
-                    const Rec me = load_rec(src.rec + p0 + k);
-                    const float us = __double2float_rn(me.x - X0), vs = __double2float_rn(me.y - Y0);
-                    const float c1f = __double2float_rn(me.c);
-                    const float gs = sqrt_apx(c1f);
-                    const float ks = rcp_apx(gs);
-                    const int ry = (int)(me.key - xs*g.ndec) - ya;
-                    S.a[k] = make_float4(us, vs*ks, ks, __int_as_float(ry));
-                    S.b[k] = make_float4(vs, c1f, gs, 0.0f);
+                // the tile's sources: raw record -> frame parameters. All records of a thread are requested at once
+                // (one round trip instead of kSrcPer: the producers' chain of dependent latencies is the critical
+                // path of the kernel)
+                {
+                    Rec sr[kSrcPer];
+#pragma unroll
+                    for (int j = 0; j < kSrcPer; ++j) {
+                        const uint32_t k = (uint32_t)(j*kProd + pt);
+                        sr[j].x = sr[j].y = 0.0; sr[j].c = 1.0; sr[j].idx = 0; sr[j].key = 0;
+                        if (k < cnt) sr[j] = load_rec(src.rec + p0 + k);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kSrcPer; ++j) {
+                        const uint32_t k = (uint32_t)(j*kProd + pt);
+                        if (k < cnt) {
+                            const float us = __double2float_rn(sr[j].x - X0), vs = __double2float_rn(sr[j].y - Y0);
+                            const float c1f = __double2float_rn(sr[j].c);
+                            const float gs = sqrt_apx(c1f);
+                            const float ks = rcp_apx(gs);
+                            const int ry = (int)(sr[j].key - xs*g.ndec) - ya;
+                            S.a[k] = make_float4(us, vs*ks, ks, __int_as_float(ry));
+                            S.b[k] = make_float4(vs, c1f, gs, 0.0f);
+                        }
+                    }
                 }
                 for (uint32_t base = 0; base < tot; base += (uint32_t)(kPB*kProd)) {
                     Rec r[kPB];
@@ -568,6 +592,23 @@ ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __res
                 }
             }
             bar_arrive(kBarFull + buf, kPThreads);
+            if (PF && t + gridDim.x < ntiles && pa.y) {
+                // The next tile's records are pulled into L2 now (its plan has landed while this tile was staged):
+                // 128-byte lines (4 records) covering the three candidate runs and the source range. No registers
+                // are held for it, and the loads of the next iteration find at least their later batches in L2.
+                const uint32_t b0 = pa.z >> 2, l0 = ((pa.z + pb.y + 3u) >> 2) - b0;
+                const uint32_t b1 = pa.w >> 2, l1 = ((pa.w + pb.z + 3u) >> 2) - b1;
+                const uint32_t b2 = pb.x >> 2, l2 = ((pb.x + pb.w + 3u) >> 2) - b2;
+                const uint32_t bs = pa.x >> 2, ls = ((pa.x + pa.y + 3u) >> 2) - bs;
+                for (uint32_t l = pt; l < l0 + l1 + l2 + ls; l += kProd) {
+                    const Rec* q;
+                    if (l < l0) q = cand.rec + 4u*(b0 + l);
+                    else if (l < l0 + l1) q = cand.rec + 4u*(b1 + (l - l0));
+                    else if (l < l0 + l1 + l2) q = cand.rec + 4u*(b2 + (l - l0 - l1));
+                    else q = src.rec + 4u*(bs + (l - l0 - l1 - l2));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+                }
+            }
         }
         return;
     }
@@ -579,6 +620,7 @@ ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __res
     const float eps_lo = __double2float_ru(g.eps_lo), eps_hi = __double2float_ru(g.eps_hi);
     const float eps = eps_lo + eps_hi + 0x1p-20f;
     const float csr = __double2float_rn(g.cs_rad);
+    const float fzxf = __double2float_ru(g.fzx), fzyf = __double2float_ru(g.fzy), sdel0 = __double2float_ru(g.stop_delta);
     uint32_t evals = 0;
     int buf = 0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, buf ^= 1) {
@@ -613,43 +655,14 @@ ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __res
         // ---- ring 0 ----
         int32_t h1 = kInfF, h2 = kInfF;
         const uint32_t self_li = SELF ? p + d1 : 0xffffffffu;
-        bool flag = false, done = !live;
+        bool flag = false;
         uint32_t mask = 0;
-        float cd = 0.0f, sdelta = 0.0f;
         if (live) {
             const uint32_t qs = S.cs[1][ry] + d1, qe = S.cs[1][ry + 1] + d1;
             scan32<SELF>(S.c, qs, qe, us, vsk, ks, self_li, h1, h2);
             evals += qe - qs;
-            const float ylo = ((float)ry - 0.5f*(float)nrows)*wyf;
-            const float dyc = vs - (ylo + 0.5f*wyf);
-            cd = sqrt_apx(fmaf(us*us*S.ccen[ry], c1f, dyc*dyc));
-            sdelta = __double2float_ru(g.stop_delta) + 1.2f*(0x1p-22f*(wxf + 2.0f*ymax) + 0x1p-19f*cd) + 0x1p-20f*csr;
-            const float hi1 = dist_hi(h1, eband), lo1 = dist_lo(h1, eband);
-            {
-                const float dhi = h1 >= kInfF ? __int_as_float(kInfF) : hi1*gs*(1.0f + 0x1p-20f);
-                const float dlo = h1 >= kInfF ? __int_as_float(kInfF) : lo1*gs*(1.0f - 0x1p-20f);
-                const int dec = stop_decision32(dlo, dhi, 0.4f*csr - 1.1f*cd, sdelta, eps_lo, eps_hi);
-                if (dec == 0) done = true; else if (dec == 2) { flag = true; done = true; }
-            }
-            if (!done) {
-                const float mx = __double2float_ru(g.fzx) + 0x1p-22f*wxf, my = __double2float_ru(g.fzy) + 0x1p-22f*ymax;
-                const float hwx = 0.5f*wxf;
-                const float sc = sqrt_apx(cminT)*(1.0f - 0x1p-20f);
-                const float ksl = ks*(1.0f - 0x1p-19f);
-                const float xl = fmaxf((us + hwx) - mx, 0.0f)*sc, xr = fmaxf((hwx - us) - mx, 0.0f)*sc;
-                const float yd = fmaxf((vs - ylo) - my, 0.0f)*ksl, yu = fmaxf(((ylo + wyf) - vs) - my, 0.0f)*ksl;
-                const float T = (h1 >= kInfF) ? __int_as_float(kInfF) : hi1*hi1*(1.0f + 2.0f*eps + 0x1p-18f);
-                const float xl2 = xl*xl, xr2 = xr*xr, yd2 = yd*yd, yu2 = yu*yu;
-                mask = (yu2 < T ? 1u : 0u) | (xr2 < T ? 2u : 0u) | (yd2 < T ? 4u : 0u) | (xl2 < T ? 8u : 0u) |
-                       (xr2 + yu2 < T ? 16u : 0u) | (xl2 + yu2 < T ? 32u : 0u) | (xl2 + yd2 < T ? 64u : 0u) |
-                       (xr2 + yd2 < T ? 128u : 0u);
-                if (ry + 1 >= nrows) mask &= ~(1u | 16u | 32u);
-                if (ry - 1 < 0) mask &= ~(4u | 64u | 128u);
-                const float wxs = wxf*(1.0f - 0x1p-20f)*sc, wys = wyf*(1.0f - 0x1p-20f)*ksl;
-                const float o = fminf(fminf((xl + wxs)*(xl + wxs), (xr + wxs)*(xr + wxs)),
-                                      fminf((yd + wys)*(yd + wys), (yu + wys)*(yu + wys)));
-                if (!(o >= T) || __popc(mask) > kQ) { flag = true; done = true; mask = 0; }
-            }
+            mask = ring0_decide(h1, us, vs, ks, gs, c1f, S.ccen[ry], ry, nrows, cminT, wxf, wyf, ymax, eband, eps, eps_lo,
+                                eps_hi, csr, fzxf, fzyf, sdel0, flag);
         }
 
         // ---- pool the surviving (source, cell) pairs (consumer-only barriers) ----
@@ -704,12 +717,6 @@ ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __res
         if (live) {
             const float hi1 = dist_hi(h1, eband);
             if (h1 >= kInfF) flag = true;
-            if (!done && !flag) {
-                const float lo1 = dist_lo(h1, eband);
-                const int dec = stop_decision32(lo1*gs*(1.0f - 0x1p-20f), hi1*gs*(1.0f + 0x1p-20f), 2.4f*csr - 1.1f*cd,
-                                                sdelta, eps_lo, eps_hi);
-                if (dec != 0) flag = true;
-            }
             if (!flag && h2 < kInfF && !(hi1*(1.0f + eps) < dist_lo(h2, eband))) flag = true;
             if (flag) {
                 const unsigned long long pos = atomicAdd(refine_count, 1ull);
@@ -781,16 +788,17 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
         XM_CUDA_TRY(cudaGetDevice(&dev));
         XM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t grid = (uint32_t)sms*4u < ntiles ? (uint32_t)sms*4u : ntiles;
-        if (self) XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn32p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Persist32)));
-        else XM_CUDA_TRY(cudaFuncSetAttribute(ring_nn32p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Persist32)));
+        // XM_NN32_PF=1: with the L2 prefetch of the next tile's records (measured: see DESIGN.md 4.2)
+        static const bool pf = [] { const char* e = getenv("XM_NN32_PF"); return e && e[0] == '1'; }();
+        auto kern = self ? (pf ? ring_nn32p_kernel<true, true> : ring_nn32p_kernel<true, false>)
+                         : (pf ? ring_nn32p_kernel<false, true> : ring_nn32p_kernel<false, false>);
+        XM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Persist32)));
         // `after`: the other direction's persistent launch, which fills every SM on its own -- running the two one
         // after the other costs nothing and lets the first lane's results leave for the host early
         if (after) XM_CUDA_TRY(cudaStreamWaitEvent(s, after, 0));
         if (k0) XM_CUDA_TRY(cudaEventRecord(k0, s));
-        if (self) ring_nn32p_kernel<true><<<grid, kPThreads, sizeof(Persist32), s>>>(g, src, cand, plan, toff + g.nra, res, refine_list,
-                                                                                      refine_count, reverse ? 1 : 0, ctr);
-        else ring_nn32p_kernel<false><<<grid, kPThreads, sizeof(Persist32), s>>>(g, src, cand, plan, toff + g.nra, res, refine_list,
-                                                                                  refine_count, reverse ? 1 : 0, ctr);
+        kern<<<grid, kPThreads, sizeof(Persist32), s>>>(g, src, cand, plan, toff + g.nra, res, refine_list, refine_count,
+                                                         reverse ? 1 : 0, ctr);
         *launches += 2;
         if (k1) XM_CUDA_TRY(cudaEventRecord(k1, s));
         if (filter_done) XM_CUDA_TRY(cudaEventRecord(filter_done, s));
