@@ -317,7 +317,9 @@ def run_gpu_arm(args):
             fwd, _, rev = qxmatch_banded(ra1, dec1, ra2, dec2, lo, params, home=bool(os.environ.get("XM_C5_HOME")))
             out = (fwd, rev)
         else:
-            out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params)
+            # reverse results stay sliced over the ranks like the forward ones (XM_C2_REPLICATE=1: on every rank)
+            out = qxmatch_sharded(ra1, dec1, ra2, dec2, lo, params,
+                                  replicate_reverse=bool(os.environ.get("XM_C2_REPLICATE")))
         if record:
             st = last_stats(local)
             for k in ("ms_forward", "ms_reverse", "ms_search", "ms_total", "ms_index", "ms_bbox", "ms_filter_fwd",
@@ -474,10 +476,11 @@ def run_e2e(args, world, rank, lo, hi, n1, n2, ra1, dec1, ra2, dec2, params, dev
                 o["rid"][:rid_.numel()].copy_(rid_, non_blocking=True)      # every rank returns its block
                 o["rd"][:rd_.numel()].copy_(rd_, non_blocking=True)
             else:
-                i_, d_, rid_, rd_ = qxmatch_sharded(a, b, ra2, dec2, lo, params)
-                if rank == 0:
-                    o["rid"].copy_(rid_, non_blocking=True)
-                    o["rd"].copy_(rd_, non_blocking=True)
+                i_, d_, rid_, rd_ = qxmatch_sharded(a, b, ra2, dec2, lo, params,
+                                                    replicate_reverse=bool(os.environ.get("XM_C2_REPLICATE")))
+                if rid_.numel() < n2 or rank == 0:       # sliced: every rank returns its block of catalog-2 rows
+                    o["rid"][:rid_.numel()].copy_(rid_, non_blocking=True)
+                    o["rd"][:rd_.numel()].copy_(rd_, non_blocking=True)
             o["id"].copy_(i_, non_blocking=True)
             o["d"].copy_(d_, non_blocking=True)
             torch.cuda.synchronize()
@@ -536,9 +539,12 @@ def parallelism_desc(args, world, hi, lo):
                 "NCCL all-to-all over NVLink (order-preserving partition kernel, halo rows to both sides); rank b matches "
                 "band b in both directions; results stay with the band, keyed by global row (XM_C5_HOME=1: forward results "
                 "return to the rows' owners by a second all-to-all)" % (hi - lo, world))
-    return ("catalog-1 rows sharded over %d ranks (%d rows each); catalog 2 NCCL-broadcast and indexed per rank; reverse "
-            "match merged by one kernel over NVLink peer memory (xm_rev_merge_p2p; NCCL all-reduce(min) when peer "
-            "mappings are unavailable)" % (world, hi - lo))
+    return ("catalog-1 rows sharded over %d ranks (%d rows each); bounding boxes of both catalogs by one 8-double "
+            "all-reduce, then catalog 2 NCCL-broadcast while the local rows of catalog 1 are indexed; catalog 2 indexed "
+            "per rank; reverse match merged by one kernel over NVLink peer memory (xm_rev_merge_p2p; NCCL "
+            "all-reduce(min) when peer mappings are unavailable), merged rows %s"
+            % (world, hi - lo, "replicated on every rank" if os.environ.get("XM_C2_REPLICATE") else
+               "left sliced over the ranks by catalog-2 row block, as the forward results are by catalog-1 row block"))
 
 
 def emit(args, world, n1, n2, lo, hi, value, ms_step, launches, clocks, stats_acc, e2e_value, e2e_steps, h2d, d2h, dt):

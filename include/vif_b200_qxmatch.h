@@ -89,6 +89,17 @@ typedef struct xm_params {
                                       /* work the same way (chunks of i AND of j, qxmatch.hpp:422-454).    */
     double   bbox1[4];                /* ra_min, ra_max, dec_min, dec_max                          */
     uint64_t fwd_begin, fwd_count, rev_begin, rev_count;
+    /* ---- appended in round 2 (older callers: struct_size): catalog 2 still on its way (xm_qxmatch_dev, cell-binned path) ---- */
+    uint64_t has_bbox2;               /* 1 (together with has_bbox1): bbox2[] is catalog 2's bounding box. */
+                                      /* The grid (qxmatch.hpp:232-267) is then known before a single row  */
+                                      /* is read: no host round trip at the head of the call, catalog 1 is */
+                                      /* indexed at once and catalog 2 as soon as it has arrived. Both     */
+                                      /* boxes and the finiteness of the rows are still verified on the    */
+                                      /* device; a violation fails the call at its end.                    */
+    double   bbox2[4];
+    void*    cat2_ready_event;        /* cudaEvent_t or NULL: nothing reads ra2/dec2 before this event     */
+                                      /* (e.g. the end of an NCCL broadcast of catalog 2 on another        */
+                                      /* stream): the broadcast overlaps the index build of catalog 1.     */
 } xm_params;
 /* xm_params p = XM_PARAMS_INIT;  -- every field zero (= reference behaviour) except the size */
 #define XM_PARAMS_INIT { sizeof(xm_params) }
@@ -212,6 +223,13 @@ int32_t xm_grid_from_bbox(const double* bbox1, const double* bbox2, uint64_t n2,
 int32_t xm_bbox_dev(const double* ra, const double* dec, uint64_t n, int32_t device, void* stream,
                     double* out, uint64_t* nonfinite, char* errbuf, uint64_t errcap);
 
+/* The same pass without a host round trip, in the layout one all-reduce(max) over the ranks of a row-sharded
+ * run wants (qxmatch.hpp:232-238 over shards): out_dev (DEVICE memory, 5 doubles) receives
+ * {-ra_min, ra_max, -dec_min, dec_max, number of non-finite rows}; an empty shard gives -inf four times.
+ * Launches on `stream` and returns without synchronising. */
+int32_t xm_bbox_neg_dev(const double* ra, const double* dec, uint64_t n, int32_t device, void* stream,
+                        double* out_dev, char* errbuf, uint64_t errcap);
+
 /* Statistics of the most recent qxmatch call on `device` (-1 = current). */
 int32_t xm_last_stats(int32_t device, xm_stats* out);
 
@@ -245,7 +263,9 @@ int32_t xm_rev_merge_unpack(uint64_t* rid, double* rd, const double* key_best, u
  *                       unmatched) as xm_qxmatch_dev returned them, and its first catalog-1 row;
  *   out[r]:             peer-mapped pointer to rank r's result buffer: n rd, then n rid.
  * The calling rank merges rows [n*rank/world, n*(rank+1)/world) -- smallest distance, smallest
- * global row id among equal distances (qxmatch.hpp:510-513) -- and stores them into EVERY out[r].
+ * global row id among equal distances (qxmatch.hpp:510-513) -- and stores them into EVERY out[r]
+ * that is not NULL (out[rank] is required; passing NULL for the peers leaves the merged reverse
+ * match sliced over the ranks and halves the NVLink traffic of the step).
  * The caller brackets the call with barriers over the ranks: all exchange buffers filled before,
  * all stores landed after (vif_b200/distributed.py uses torch symmetric memory for both).
  * world <= XM_MAX_PEERS. Launches on `stream` and returns without synchronising.

@@ -37,6 +37,25 @@ for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 1
     if rank == 0:
         print(("OK  " if flag.item() else "FAIL"), name, "world", world, flush=True)
     ok_all &= bool(flag.item())
+    if name in ("binned", "ties_across_shards", "binned_nccl_merge"):
+        # merged reverse match left sliced over the ranks; and the round-1 order of the collectives
+        lo2, hi2 = shard_bounds(n2, world, rank)
+        for label, env in (("sliced", None), ("early_bcast", "XM_DIST_EARLY_BCAST")):
+            if env:
+                os.environ[env] = "1"
+            if rank != 0:
+                ra2.zero_(); dec2.zero_()
+            _, _, rs, ds = qxmatch_sharded(full1[0][lo:hi].contiguous(), full1[1][lo:hi].contiguous(), ra2, dec2, lo,
+                                           QxmatchParams(device=local, **kw), replicate_reverse=(label != "sliced"))
+            if env:
+                del os.environ[env]
+            want = (ref.rid[lo2:hi2], ref.rd[lo2:hi2]) if label == "sliced" else (ref.rid, ref.rd)
+            ok = torch.equal(rs, want[0]) and torch.equal(ds.nan_to_num(-1.0), want[1].nan_to_num(-1.0))
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(("OK  " if flag.item() else "FAIL"), name + "_" + label, "world", world, flush=True)
+            ok_all &= bool(flag.item())
 # declination-band decomposition (qxmatch_banded): both directions sharded; must equal the single-GPU exact search
 from vif_b200.distributed import qxmatch_banded
 for name, n1, n2, halo in (("banded", 2_000_000, 1_000_000, None), ("banded_dups", 600_000, 500_000, None),

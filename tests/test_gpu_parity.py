@@ -453,6 +453,62 @@ def test_row_ranges_equal_slices_of_the_unranged_result(kw):
             assert torch.equal(part.rid, whole.rid[rb:rb + rc]) and torch.equal(part.rd, whole.rd[rb:rb + rc])
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(nth=3)], ids=["nth1", "nth3"])
+def test_promised_boxes_and_late_catalog2(kw):
+    """Row-sharded multi-GPU runs hand the library both bounding boxes (they come out of one all-reduce) and the
+    event that ends the broadcast of catalog 2 (xm_params.bbox2 / cat2_ready_event): no host round trip at the head
+    of the call, catalog 1 indexed while catalog 2 is still in flight. Same grid (qxmatch.hpp:232-267 from the same
+    boxes), so the same result bit for bit; a box that does not hold, or a NaN row, fails the call at its end."""
+    from vif_b200.qxmatch import QxmatchParams
+    n1, n2 = 150_000, 130_000
+    a1, b1 = [torch.from_numpy(x).cuda() for x in G.c2(91, n1)]
+    h2 = [torch.from_numpy(x).pin_memory() for x in G.c2(92, n2)]
+    a2, b2 = h2[0].cuda(), h2[1].cuda()
+    whole = qxmatch(a1, b1, a2, b2, **kw)
+    bb1 = (float(a1.min()), float(a1.max()), float(b1.min()), float(b1.max()))
+    bb2 = (float(a2.min()), float(a2.max()), float(b2.min()), float(b2.max()))
+    # catalog 2 arrives on a side stream behind a long-running kernel: the call is issued before it has landed
+    late = [torch.zeros_like(a2), torch.zeros_like(b2)]
+    side = torch.cuda.Stream()
+    ready = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(20_000_000)                       # ~10 ms
+        late[0].copy_(h2[0], non_blocking=True)
+        late[1].copy_(h2[1], non_blocking=True)
+        ready.record(side)
+    p = QxmatchParams(bbox1=bb1, bbox2=bb2, cat2_ready_event=int(ready.cuda_event), **kw)
+    got = qxmatch(a1, b1, late[0], late[1], params=p)
+    assert torch.equal(got.id, whole.id) and torch.equal(got.rid, whole.rid)
+    assert torch.equal(got.d.nan_to_num(-1.0), whole.d.nan_to_num(-1.0)) and torch.equal(got.rd, whole.rd)
+    assert got.stats["grid"] == whole.stats["grid"]
+    # without the boxes the event alone orders the whole call behind catalog 2
+    late2 = [torch.zeros_like(a2), torch.zeros_like(b2)]
+    ready2 = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(20_000_000)
+        late2[0].copy_(h2[0], non_blocking=True)
+        late2[1].copy_(h2[1], non_blocking=True)
+        ready2.record(side)
+    got2 = qxmatch(a1, b1, late2[0], late2[1], params=QxmatchParams(cat2_ready_event=int(ready2.cuda_event), **kw))
+    assert torch.equal(got2.id, whole.id) and torch.equal(got2.rid, whole.rid)
+    # a promise that does not hold
+    # (the boxes define the grid, qxmatch.hpp:232-267; what is verified is that every row is finite and on it)
+    with pytest.raises(QxmatchError, match="catalog 2: .* promised bounding box"):
+        qxmatch(a1[a1 > bb1[0] + 1.0], b1[a1 > bb1[0] + 1.0], a2, b2,
+                params=QxmatchParams(bbox1=(bb1[0] + 1.0, bb1[1], bb1[2], bb1[3]),
+                                     bbox2=(bb2[0] + 1.0, bb2[1], bb2[2], bb2[3]), **kw))
+    bad = a2.clone(); bad[7] = float("nan")
+    with pytest.raises(QxmatchError, match="catalog 2: 1 rows are not finite or lie outside"):
+        qxmatch(a1, b1, bad, b2, params=QxmatchParams(bbox1=bb1, bbox2=bb2, **kw))
+    bad1 = a1.clone(); bad1[3] = float("inf"); bad1[11] = -1e6
+    with pytest.raises(QxmatchError, match="catalog 1: 2 rows are not finite or lie outside"):
+        qxmatch(bad1, b1, a2, b2, params=QxmatchParams(bbox1=bb1, bbox2=bb2, **kw))
+    with pytest.raises(QxmatchError, match="second RA and Dec coordinates contain invalid values"):
+        qxmatch(a1, b1, bad, b2, **kw)                      # the measured-box flow reports as the reference does
+    again = qxmatch(a1, b1, a2, b2, **kw)                   # the device is in order after the failed calls
+    assert torch.equal(again.id, whole.id)
+
+
 # ---- the FP64 filter kernel against its numpy model (tests/ring_filter_model.py) ----------------------------
 @pytest.mark.parametrize("name", ["c1_box", "tall_dec_field", "high_dec_box", "displaced_copies", "large_cells", "self"])
 def test_fp64_filter_flags_the_rows_its_model_flags(oracle, name, monkeypatch):

@@ -17,7 +17,8 @@ class XmParams(C.Structure):
                 ("brute_force", C.c_uint8), ("no_mirror", C.c_uint8), ("linear", C.c_uint8),
                 ("has_bbox1", C.c_uint8), ("exact_only", C.c_uint8), ("exact_grid", C.c_uint8),
                 ("device", i32), ("has_ranges", i32), ("bbox1", f64 * 4),
-                ("fwd_begin", u64), ("fwd_count", u64), ("rev_begin", u64), ("rev_count", u64)]
+                ("fwd_begin", u64), ("fwd_count", u64), ("rev_begin", u64), ("rev_count", u64),
+                ("has_bbox2", u64), ("bbox2", f64 * 4), ("cat2_ready_event", C.c_void_p)]
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
@@ -51,7 +52,7 @@ class XmStats(C.Structure):
 
 
 # every symbol include/vif_b200_qxmatch.h declares (tests check the export list against the header)
-SYMBOLS = ["xm_libm_model", "xm_libm_eval_host", "xm_libm_eval_dev", "xm_band_partition_dev", "xm_band_finish_dev", "xm_band_home_dev", "xm_fp64_peak", "xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
+SYMBOLS = ["xm_bbox_neg_dev", "xm_libm_model", "xm_libm_eval_host", "xm_libm_eval_dev", "xm_band_partition_dev", "xm_band_finish_dev", "xm_band_home_dev", "xm_fp64_peak", "xm_version", "xm_init", "xm_shutdown", "xm_release_memory", "xm_rev_merge_p2p", "xm_angdist_dev", "xm_angdist_less_dev", "xm_qdist_dev", "xm_qxmatch_f64", "xm_qxmatch_dev",
            "xm_grid_from_bbox", "xm_bbox_dev", "xm_last_stats", "xm_sort_pairs_dev", "xm_ring_entries",
            "xm_rev_merge_pack", "xm_rev_merge_mask", "xm_rev_merge_unpack", "xm_clean_best_dev"]
 
@@ -85,6 +86,8 @@ def load():
     lib.xm_grid_from_bbox.argtypes = [dp, dp, u64, u64, i32, C.POINTER(XmGrid)]
     lib.xm_bbox_dev.restype = i32
     lib.xm_bbox_dev.argtypes = [vp, vp, u64, i32, vp, dp, up, C.c_char_p, u64]
+    lib.xm_bbox_neg_dev.restype = i32
+    lib.xm_bbox_neg_dev.argtypes = [vp, vp, u64, i32, vp, vp, C.c_char_p, u64]
     lib.xm_band_partition_dev.restype = i32
     lib.xm_band_partition_dev.argtypes = [C.c_void_p, C.c_void_p, u64, u64, C.POINTER(f64), i32, f64, i32, C.c_void_p, u64,
                                           C.c_void_p, C.POINTER(u64), i32, C.c_void_p, C.c_char_p, u64]

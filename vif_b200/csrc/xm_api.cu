@@ -199,10 +199,13 @@ struct SortedCat {
 
 // One catalog -> cell-ordered records + CSR offsets. use_bucket: counting-sort placement
 // (xm_bucket.cu); otherwise keys -> stable radix sort -> gather (no limit on cell occupancy).
-int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
+int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridView& g_in,
                     uint32_t ncell, bool use_bucket, bool order_cells, uint32_t* overflow, SortedCat& out,
                     cudaStream_t s,
-                    Error& err, uint64_t* launches, cudaEvent_t ev_keys, cudaEvent_t ev_sort) {
+                    Error& err, uint64_t* launches, cudaEvent_t ev_keys, cudaEvent_t ev_sort,
+                    unsigned long long* off_grid = nullptr) {
+    GridView g = g_in;
+    g.off_grid = off_grid;
     XM_CUDA_TRY(out.rec.alloc((size_t)n*sizeof(Rec), s));
     XM_CUDA_TRY(out.cell.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
     int32_t rc;
@@ -237,7 +240,7 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
         if (ev_sort) XM_CUDA_TRY(cudaEventRecord(ev_sort, s));
         rc = launch_cells_and_gather(key.as<uint32_t>(), perm.as<uint32_t>(), ra, dec, n, ncell,
                                      g.linear != 0, out.rec.as<Rec>(), out.cell.as<uint32_t>(), s, err,
-                                     launches, g.sin_model);
+                                     launches, g.sin_model, g);
         if (rc) return rc;
     }
     out.view.rec = out.rec.as<Rec>(); out.view.cstart = out.cell.as<uint32_t>(); out.view.n = n;
@@ -360,24 +363,44 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
 
     // bounding boxes + finiteness (qxmatch.hpp:146-149, 232-235)
     const bool same_cat = (ra1 == ra2 && dec1 == dec2 && n1 == n2);
-    if ((rc = launch_bbox(ra1, dec1, n1, ctx->d_small, s, err, &launches))) return rc;
-    if (!same_cat && (rc = launch_bbox(ra2, dec2, n2, ctx->d_small + 5, s, err, &launches))) return rc;
-    XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_small, ctx->d_small, 10*sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, s));
-    XM_CUDA_TRY(cudaEventRecord(ev[1], s));
-    XM_CUDA_TRY(cudaStreamSynchronize(s));
-    if (same_cat) memcpy(ctx->h_small + 5, ctx->h_small, 5*sizeof(unsigned long long));
-    if (ctx->h_small[4])
-        return fail(err, XM_ERR_NONFINITE_1, "first RA and Dec coordinates contain invalid values (infinite or NaN)");
-    if (ctx->h_small[9])
-        return fail(err, XM_ERR_NONFINITE_2, "second RA and Dec coordinates contain invalid values (infinite or NaN)");
+    cudaEvent_t cat2_ready = (cudaEvent_t)P.cat2_ready_event;
+    // Both boxes promised by the caller (row-sharded multi-GPU runs: the boxes come out of one all-reduce
+    // while catalog 2 is still being broadcast): the grid is known without reading a row, so the call does
+    // not start with a bounding-box pass and a host round trip, and lane s2 alone waits for catalog 2. That
+    // the promise held -- every row finite and on the grid -- is checked by the count pass of the index build
+    // (SearchCounters::off_grid1/2) and reported when the call ends. Only where the reference's grid is feasible.
+    bool promised = P.has_bbox1 && P.has_bbox2 && !P.brute_force && !same_cat && !ranged;
+    if (promised) {
+        xm_grid Gp;
+        grid_from_bbox(P.bbox1, P.bbox2, n2, nth, linear, &Gp);
+        if (Gp.nra == 0 || Gp.ndec == 0 || Gp.nra > 0x7fffffffull || Gp.ndec > 0x7fffffffull || Gp.nra*Gp.ndec > XM_MAX_CELLS)
+            promised = false;
+    }
     double bb1[4], bb2[4];
-    for (int k = 0; k < 4; ++k) { bb1[k] = ord2f(ctx->h_small[k]); bb2[k] = ord2f(ctx->h_small[5 + k]); }
-    if (P.has_bbox1) {
-        // the promised box must contain the rows passed
-        if (P.bbox1[0] > bb1[0] || P.bbox1[1] < bb1[1] || P.bbox1[2] > bb1[2] || P.bbox1[3] < bb1[3])
-            return fail(err, XM_ERR_INVALID_ARG, "bbox1 does not contain the catalog-1 rows passed");
-        for (int k = 0; k < 4; ++k) bb1[k] = P.bbox1[k];
+    if (promised) {
+        XM_CUDA_TRY(cudaEventRecord(ev[1], s));
+        for (int k = 0; k < 4; ++k) { bb1[k] = P.bbox1[k]; bb2[k] = P.bbox2[k]; }
+    } else {
+        if (cat2_ready) XM_CUDA_TRY(cudaStreamWaitEvent(s, cat2_ready, 0));
+        if ((rc = launch_bbox(ra1, dec1, n1, ctx->d_small, s, err, &launches))) return rc;
+        if (!same_cat && (rc = launch_bbox(ra2, dec2, n2, ctx->d_small + 5, s, err, &launches))) return rc;
+        XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_small, ctx->d_small, 10*sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, s));
+        XM_CUDA_TRY(cudaEventRecord(ev[1], s));
+        XM_CUDA_TRY(cudaStreamSynchronize(s));
+        if (same_cat) memcpy(ctx->h_small + 5, ctx->h_small, 5*sizeof(unsigned long long));
+        const unsigned long long* h = ctx->h_small;
+        if (h[4])
+            return fail(err, XM_ERR_NONFINITE_1, "first RA and Dec coordinates contain invalid values (infinite or NaN)");
+        if (h[9])
+            return fail(err, XM_ERR_NONFINITE_2, "second RA and Dec coordinates contain invalid values (infinite or NaN)");
+        for (int k = 0; k < 4; ++k) { bb1[k] = ord2f(h[k]); bb2[k] = ord2f(h[5 + k]); }
+        if (P.has_bbox1) {
+            // the promised box must contain the rows passed
+            if (P.bbox1[0] > bb1[0] || P.bbox1[1] < bb1[1] || P.bbox1[2] > bb1[2] || P.bbox1[3] < bb1[3])
+                return fail(err, XM_ERR_INVALID_ARG, "bbox1 does not contain the catalog-1 rows passed");
+            for (int k = 0; k < 4; ++k) bb1[k] = P.bbox1[k];
+        }
     }
 
     XM_CUDA_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(SearchCounters), s));
@@ -535,13 +558,16 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         cudaEvent_t* sev = ctx->sync_ev;
         XM_CUDA_TRY(cudaEventRecord(sev[0], s));                       // inputs / row tables ready
         XM_CUDA_TRY(cudaStreamWaitEvent(s2, sev[0], 0));
+        if (promised && cat2_ready) XM_CUDA_TRY(cudaStreamWaitEvent(s2, cat2_ready, 0));   // lane s2 alone waits for catalog 2
         SortedCat s1, s2cat;
         if ((rc = build_index(ra1, dec1, (uint32_t)n1, g, ncell, use_bucket, !unordered,
-                              &ctx->d_ctr->index_overflow, s1, s, err, &launches, ev[2], ev[3]))) return rc;
+                              &ctx->d_ctr->index_overflow, s1, s, err, &launches, ev[2], ev[3],
+                              &ctx->d_ctr->off_grid1))) return rc;
         const CatView* v2 = &s1.view;
         if (!same_cat) {
             if ((rc = build_index(ra2, dec2, (uint32_t)n2, g, ncell, use_bucket, !unordered,
-                                  &ctx->d_ctr->index_overflow, s2cat, s2, err, &launches, nullptr, nullptr))) return rc;
+                                  &ctx->d_ctr->index_overflow, s2cat, s2, err, &launches, nullptr, nullptr,
+                                  &ctx->d_ctr->off_grid2))) return rc;
             v2 = &s2cat.view;
         }
         // partitioned run: the searched rows are blocks of the catalogs, indexed on their own; the
@@ -698,6 +724,15 @@ finish:
     }
     st.rows_ambiguous = ctx->h_ctr->ambiguous;
     st.rows_refined_fwd = ctx->h_ctr->refine_fwd; st.rows_refined_rev = ctx->h_ctr->refine_rev;
+    if (promised) {
+        // did the promise hold? (counted by the index build, copied with the other counters)
+        if (ctx->h_ctr->off_grid1)
+            return fail(err, XM_ERR_INVALID_ARG, "catalog 1: %llu rows are not finite or lie outside the promised bounding box (bbox1)",
+                        (unsigned long long)ctx->h_ctr->off_grid1);
+        if (ctx->h_ctr->off_grid2)
+            return fail(err, XM_ERR_INVALID_ARG, "catalog 2: %llu rows are not finite or lie outside the promised bounding box (bbox2)",
+                        (unsigned long long)ctx->h_ctr->off_grid2);
+    }
     if (P.verbose) {
         printf("[vif_b200] qxmatch n1=%llu n2=%llu nth=%llu %s: %.3f ms on device (index %.3f, forward %.3f, "
                "reverse %.3f), %llu kernel launches\n", (unsigned long long)n1, (unsigned long long)n2,
@@ -1016,6 +1051,26 @@ int32_t xm_bbox_dev(const double* ra, const double* dec, uint64_t n, int32_t dev
     return rc;
 }
 
+int32_t xm_bbox_neg_dev(const double* ra, const double* dec, uint64_t n, int32_t device, void* stream,
+                        double* out_dev, char* errbuf, uint64_t errcap) {
+    Error err;
+    Context* ctx = nullptr;
+    int32_t rc = (!out_dev || (n && (!ra || !dec))) ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
+    if (!rc) rc = get_context(device, &ctx, err);
+    if (!rc) {
+        auto body = [&]() -> int32_t {
+            DeviceGuard dg;
+            XM_CUDA_TRY(dg.set(ctx->device));
+            cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+            uint64_t launches = 0;
+            return launch_bbox_neg(ra, dec, n, out_dev, s, err, &launches);
+        };
+        rc = body();
+    }
+    if (rc) copy_err(err, errbuf, errcap);
+    return rc;
+}
+
 int32_t xm_last_stats(int32_t device, xm_stats* out) {
     if (!out) return XM_ERR_INVALID_ARG;
     Error err;
@@ -1102,7 +1157,7 @@ int32_t xm_rev_merge_p2p(const void* const* exch, void* const* out, uint64_t n, 
     int32_t rc = (!exch || !out || world < 1 || world > XM_MAX_PEERS || rank < 0 || rank >= world)
                      ? fail(err, XM_ERR_INVALID_ARG, "bad argument") : XM_OK;
     for (int r = 0; !rc && r < world; ++r)
-        if (n && (!exch[r] || !out[r])) rc = fail(err, XM_ERR_INVALID_ARG, "null peer pointer");
+        if (n && (!exch[r] || (r == rank && !out[r]))) rc = fail(err, XM_ERR_INVALID_ARG, "null peer pointer");
     if (!rc) rc = get_context(device, &ctx, err);
     if (!rc) {
         auto body = [&]() -> int32_t {

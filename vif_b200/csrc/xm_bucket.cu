@@ -25,10 +25,14 @@ namespace {
 constexpr int kThreads = 256;
 constexpr uint32_t kMaxCellSort = 4096;
 
-__device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridView& g) {
+// on_grid: the row is finite and falls on the grid. With bounding boxes measured by the library that is always so
+// (the grid is padded by a cell, qxmatch.hpp:258-262); with boxes promised by the caller it is the check that the
+// promise held (rows are clamped onto the grid so that nothing is written out of bounds, and the call fails).
+__device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridView& g, bool* on_grid = nullptr) {
     // qxmatch.hpp:278-279
     const double fx = floor(__ddiv_rn(__dsub_rn(ra, g.rra0), g.dra));
     const double fy = floor(__ddiv_rn(__dsub_rn(dec, g.rdec0), g.ddec));
+    if (on_grid) *on_grid = fx >= 0 && fx < (double)g.nra && fy >= 0 && fy < (double)g.ndec;     // false for NaN
     const uint32_t ix = fx < 0 ? 0u : (fx >= (double)g.nra ? g.nra - 1 : (uint32_t)fx);
     const uint32_t iy = fy < 0 ? 0u : (fy >= (double)g.ndec ? g.ndec - 1 : (uint32_t)fy);
     return ix*g.ndec + iy;
@@ -49,11 +53,15 @@ count_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint
         d[k] = i < n ? __ldg(dec + i) : 0.0;
     }
     uint32_t rk[kRows];
+    uint32_t off = 0;
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
         const uint32_t i = base + k*kThreads;
-        rk[k] = i < n ? atomicAdd(count + cell_key(r[k], d[k], g), 1u) : 0u;
+        bool on = true;
+        rk[k] = i < n ? atomicAdd(count + cell_key(r[k], d[k], g, &on), 1u) : 0u;
+        off += (i < n && !on) ? 1u : 0u;
     }
+    if (off && g.off_grid) atomicAdd(g.off_grid, (unsigned long long)off);
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
         const uint32_t i = base + k*kThreads;
@@ -136,8 +144,16 @@ place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint
     }
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-        key[k] = cell_key(r[k], d[k], g);
+        bool on = true;
+        key[k] = cell_key(r[k], d[k], g, &on);
         slot[k] = __ldg(cstart + key[k]) + rk[k];
+        if (!on) {
+            // a row that is not finite or off the grid (promised bounding boxes that did not hold: the call fails
+            // when it ends) is moved to the centre of the cell it was clamped to, so that every kernel downstream
+            // sees coordinates that agree with the index
+            r[k] = g.rra0 + ((double)(key[k]/g.ndec) + 0.5)*g.dra;
+            d[k] = g.rdec0 + ((double)(key[k]%g.ndec) + 0.5)*g.ddec;
+        }
     }
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {

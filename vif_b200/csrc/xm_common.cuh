@@ -46,12 +46,15 @@ struct GridView {
     int32_t  linear;
     int32_t  sin_model;       // 1: glibc __sin_fma Taylor branch, 2: non-FMA build of the same
     uint32_t self_off;        // partitioned self match: source row r is candidate row r + self_off
+    unsigned long long* off_grid;   // index build: counter of rows that do not fall on the grid (may be null)
 };
 
 struct SearchCounters {       // device counters, zeroed per call
     unsigned long long evals_fwd, evals_rev, ambiguous, refine_fwd, refine_rev;
     unsigned int index_overflow;  // cells too large for the bucket index's in-cell ordering
     unsigned int pad;
+    unsigned long long off_grid1, off_grid2;   // rows of catalog 1 / 2 that are not finite or fall outside the grid
+                                               // (only possible when the caller promised the bounding boxes)
 };
 
 // ---- error plumbing ------------------------------------------------------------------------
@@ -115,12 +118,14 @@ int32_t launch_merge_p2p(const void* const* exch, void* const* out, uint64_t n, 
 int32_t launch_merge_step(int which, unsigned long long* rid, double* rd, const double* ka, const double* kb,
                           double* key_out, uint64_t n, unsigned long long off, double unmatched,
                           cudaStream_t s, Error& err);
+int32_t launch_bbox_neg(const double* ra, const double* dec, uint64_t n, double* out5, cudaStream_t s, Error& err,
+                        uint64_t* launches);
 int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridView& g,
                     uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches);
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
                                 Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
-                                uint64_t* launches, int model);
+                                uint64_t* launches, int model, const GridView& g);
 // xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
 size_t  bucket_scan_aux_bytes(uint32_t ncell);
 void    launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches);

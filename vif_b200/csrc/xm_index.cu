@@ -74,11 +74,12 @@ __global__ void bbox_init_kernel(unsigned long long* out5) {
 __global__ void __launch_bounds__(kThreads)
 keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, double rra0,
             double rdec0, double dra, double ddec, uint32_t nra, uint32_t ndec,
-            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* off_grid) {
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double fx = floor(__ddiv_rn(__dsub_rn(__ldg(ra + i), rra0), dra));
     const double fy = floor(__ddiv_rn(__dsub_rn(__ldg(dec + i), rdec0), ddec));
+    if (off_grid && !(fx >= 0 && fx < (double)nra && fy >= 0 && fy < (double)ndec)) atomicAdd(off_grid, 1ull);
     // with has_bbox1 a caller could hand us rows outside the box it promised: clamp instead of
     // writing out of bounds (rows inside the box are unaffected)
     uint32_t ix = fx < 0 ? 0u : (fx >= (double)nra ? nra - 1 : (uint32_t)fx);
@@ -91,13 +92,21 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
 __global__ void __launch_bounds__(kThreads)
 cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
                     const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
-                    int linear, int model, Rec* __restrict__ rec) {
+                    int linear, int model, double rra0, double rdec0, double dra, double ddec, uint32_t nra,
+                    uint32_t ndec, Rec* __restrict__ rec) {
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t i = perm[p];
-    const double r = __ldg(ra + i), d = __ldg(dec + i);
+    double r = __ldg(ra + i), d = __ldg(dec + i);
     Rec out;
     out.idx = i; out.key = skeys[p];
+    {   // rows that are not finite or off the grid: to the centre of the cell they were clamped to (see place_kernel)
+        const double fx = floor(__ddiv_rn(__dsub_rn(r, rra0), dra)), fy = floor(__ddiv_rn(__dsub_rn(d, rdec0), ddec));
+        if (!(fx >= 0 && fx < (double)nra && fy >= 0 && fy < (double)ndec)) {
+            r = rra0 + ((double)(out.key/ndec) + 0.5)*dra;
+            d = rdec0 + ((double)(out.key%ndec) + 0.5)*ddec;
+        }
+    }
     if (linear) {
         out.x = r; out.y = d; out.c = 1.0;
     } else {
@@ -179,6 +188,7 @@ merge_p2p_kernel(PeerSet P, uint64_t n, uint64_t lo, uint64_t hi, int world, dou
         const double od = ok ? bk : unmatched;
         const unsigned long long oi = ok ? br : ~0ull;
         for (int r = 0; r < world; ++r) {
+            if (P.out[r] == nullptr) continue;          // sliced result: the merged rows stay with their rank
             P.out[r][j] = od;
             reinterpret_cast<unsigned long long*>(P.out[r])[n + j] = oi;
         }
@@ -224,10 +234,40 @@ int32_t launch_bbox(const double* ra, const double* dec, uint64_t n, unsigned lo
     return XM_OK;
 }
 
+// in place: {ord(min ra), ord(max ra), ord(min dec), ord(max dec), bad} -> doubles {-min ra, max ra, -min dec, max dec, bad}
+__global__ void bbox_neg_kernel(unsigned long long* io5) {
+    const unsigned long long o0 = io5[0], o1 = io5[1], o2 = io5[2], o3 = io5[3], bad = io5[4];
+    auto ord2d = [](unsigned long long o) {
+        const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+        return __longlong_as_double((long long)b);
+    };
+    double* out = reinterpret_cast<double*>(io5);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const bool empty = o0 == ~0ull && o1 == 0ull;           // no finite row seen: neutral element of max
+    out[0] = empty ? -inf : -ord2d(o0); out[1] = empty ? -inf : ord2d(o1);
+    out[2] = empty ? -inf : -ord2d(o2); out[3] = empty ? -inf : ord2d(o3);
+    out[4] = (double)bad;
+}
+
+int32_t launch_bbox_neg(const double* ra, const double* dec, uint64_t n, double* out5, cudaStream_t s, Error& err,
+                        uint64_t* launches) {
+    unsigned long long* io = reinterpret_cast<unsigned long long*>(out5);
+    bbox_init_kernel<<<1, 1, 0, s>>>(io);
+    if (n) {
+        uint64_t blocks = (n + kThreads*8 - 1)/(kThreads*8);
+        if (blocks > 148*16) blocks = 148*16;
+        bbox_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(ra, dec, n, io);
+    }
+    bbox_neg_kernel<<<1, 1, 0, s>>>(io);
+    *launches += 3;
+    XM_CUDA_TRY(cudaGetLastError());
+    return XM_OK;
+}
+
 int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridView& g,
                     uint32_t* keys, uint32_t* vals, cudaStream_t s, Error& err, uint64_t* launches) {
     keys_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(ra, dec, n, g.rra0, g.rdec0, g.dra,
-                                                                g.ddec, g.nra, g.ndec, keys, vals);
+                                                                g.ddec, g.nra, g.ndec, keys, vals, g.off_grid);
     *launches += 1;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;
@@ -236,10 +276,11 @@ int32_t launch_keys(const double* ra, const double* dec, uint32_t n, const GridV
 int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, const double* ra,
                                 const double* dec, uint32_t n, uint32_t ncell, bool linear,
                                 Rec* rec, uint32_t* cstart, cudaStream_t s, Error& err,
-                                uint64_t* launches, int model) {
+                                uint64_t* launches, int model, const GridView& g) {
     cell_offsets_kernel<<<(ncell + 1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, n, ncell, cstart);
     cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
-                                                                        linear ? 1 : 0, model, rec);
+                                                                        linear ? 1 : 0, model, g.rra0, g.rdec0, g.dra,
+                                                                        g.ddec, g.nra, g.ndec, rec);
     *launches += 2;
     XM_CUDA_TRY(cudaGetLastError());
     return XM_OK;

@@ -49,13 +49,31 @@ def _cuda_bbox(ra, dec):
     return [out[0], out[1], out[2], out[3]]
 
 
+def _cuda_bbox_neg(ra, dec, out):
+    """xm_bbox_neg_dev: {-ra_min, ra_max, -dec_min, dec_max, non-finite rows} into the device tensor `out`
+    (5 doubles), on torch's current stream, without a host round trip."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    err = C.create_string_buffer(512)
+    stream = torch.cuda.current_stream(out.device)
+    n = ra.numel()
+    rc = _lib.load().xm_bbox_neg_dev(ra.data_ptr() if n else None, dec.data_ptr() if n else None, n,
+                                     out.device.index or 0, stream.cuda_stream, out.data_ptr(), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+
+
 def _cuda_compute(ra1, dec1, ra2, dec2, params, out=None):
     from .qxmatch import qxmatch
     return qxmatch(ra1, dec1, ra2, dec2, params=params, out=out)
 
 
+_COMM = {}          # device index -> side stream that carries the broadcast of catalog 2
+
+
 def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=None, src=0,
-                    broadcast_cat2=True, compute=None, bbox=None):
+                    broadcast_cat2=True, compute=None, bbox=None, replicate_reverse=True):
     """Runs one rank's part of a row-sharded qxmatch.
 
     ra1_local/dec1_local: this rank's rows [row_offset, row_offset + len) of catalog 1.
@@ -63,14 +81,25 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     broadcast_cat2). Returns (id_local, d_local, rid, rd): forward results for the local rows,
     reverse results replicated on every rank with GLOBAL catalog-1 row ids. Ids are int64 bit
     patterns (NPOS == -1) as in the single-GPU device path.
+    replicate_reverse=False leaves the merged reverse match sliced over the ranks, as the forward
+    match is: rid / rd then cover catalog-2 rows [shard_bounds(n2, world, rank)) only (half the
+    NVLink traffic of the merge).
+
+    On GPUs the call is laid out so that nothing waits for catalog 2 longer than it must:
+    the bounding boxes of BOTH catalogs come out of one 8-element all-reduce (rank `src` knows catalog 2),
+    the broadcast of catalog 2 is issued behind it on a side stream, and the library is told the boxes
+    (xm_params.bbox1 / bbox2) and the event that marks the end of the broadcast
+    (xm_params.cat2_ready_event): it indexes the local rows of catalog 1 while catalog 2 is in flight.
     """
     import torch
     import torch.distributed as dist
     from .qxmatch import QxmatchParams
 
+    on_gpu = ra1_local.is_cuda and compute is None
     compute = compute or _cuda_compute
     bbox = bbox or _cuda_bbox
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     timing = os.environ.get("XM_DIST_TIMING") and ra1_local.is_cuda
     marks = []
 
@@ -83,26 +112,65 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
     if params.self:
         raise ValueError("self-match shards catalog 1 against itself: pass the full catalog as "
                          "catalog 2 and self=False with an explicit id offset instead")
+    late_cat2 = bool(broadcast_cat2 and world > 1 and on_gpu and not params.brute_force
+                     and not os.environ.get("XM_DIST_EARLY_BCAST"))
     pending = []
-    if broadcast_cat2 and world > 1:          # in flight while the bounding box makes its two host round trips
+    if broadcast_cat2 and world > 1 and not late_cat2:     # in flight while the bounding box is exchanged
         pending = [dist.broadcast(ra2, src=src, group=group, async_op=True),
                    dist.broadcast(dec2, src=src, group=group, async_op=True)]
 
     # global bounding box of catalog 1 (qxmatch.hpp:232-238): one all-reduce(max) on
-    # (-ra_min, ra_max, -dec_min, dec_max)
-    bb = bbox(ra1_local, dec1_local)
-    ext = torch.tensor([-bb[0], bb[1], -bb[2], bb[3]], dtype=torch.float64, device=ra1_local.device)
-    if world > 1:
-        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
-    ext = ext.tolist()
+    # (-ra_min, ra_max, -dec_min, dec_max); with late_cat2 catalog 2's box rides along (known to `src` only)
+    ready = None
+    if late_cat2 and bbox is _cuda_bbox:
+        # Everything stays on the device until the one read after the all-reduce, and everything runs on ONE side
+        # stream (never torch's legacy default stream: handed that handle, the library would launch on a stream of
+        # its own, unordered with the tensors made here): two bounding-box passes (the second on `src` only) into
+        # {-min, max, -min, max, bad rows} x 2, the 10-double all-reduce(max), then the broadcast of catalog 2 --
+        # behind the all-reduce, because collectives of one communicator run in the order they were issued.
+        dev = ra1_local.device
+        comm = _COMM.get(dev.index or 0)
+        if comm is None:
+            comm = _COMM[dev.index or 0] = torch.cuda.Stream(device=dev)
+        comm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(comm):
+            ext = torch.full((10,), float("-inf"), dtype=torch.float64, device=dev)
+            _cuda_bbox_neg(ra1_local, dec1_local, ext[0:5])
+            if rank == src:
+                _cuda_bbox_neg(ra2, dec2, ext[5:10])
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+            works = [dist.broadcast(ra2, src=src, group=group, async_op=True),
+                     dist.broadcast(dec2, src=src, group=group, async_op=True)]
+            e = ext.tolist()                   # the one host round trip: waits for the all-reduce, not the broadcast
+            for w in works:
+                w.wait()                       # orders `comm` behind NCCL's stream; does not block the host
+            ready = torch.cuda.Event()
+            ready.record(comm)
+        if e[4] > 0 or e[9] > 0:
+            raise RuntimeError("%s RA and Dec coordinates contain invalid values (infinite or NaN)"
+                               % ("first" if e[4] > 0 else "second"))
+        ext = e[0:4] + e[5:9]
+        extra = {"bbox1": (-ext[0], ext[1], -ext[2], ext[3]), "bbox2": (-ext[4], ext[5], -ext[6], ext[7]),
+                 "cat2_ready_event": int(ready.cuda_event)}
+    else:
+        late_cat2 = False
+        bb = bbox(ra1_local, dec1_local)
+        ext = torch.tensor([-bb[0], bb[1], -bb[2], bb[3]], dtype=torch.float64, device=ra1_local.device)
+        if world > 1:
+            if broadcast_cat2 and not pending:
+                pending = [dist.broadcast(ra2, src=src, group=group, async_op=True),
+                           dist.broadcast(dec2, src=src, group=group, async_op=True)]
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+        ext = ext.tolist()
+        extra = {"bbox1": (-ext[0], ext[1], -ext[2], ext[3])}
     for w in pending:
         w.wait()
-    mark("broadcast+bbox")
-    p = QxmatchParams(**{**params.__dict__, "bbox1": (-ext[0], ext[1], -ext[2], ext[3])})
+    mark("bbox" if late_cat2 else "broadcast+bbox")
+    p = QxmatchParams(**{**params.__dict__, **extra})
 
     # the reverse results go straight into the peer-mapped exchange buffer of the merge when there is one
     ent = None
-    if compute is _cuda_compute and world > 1 and not p.no_mirror:
+    if on_gpu and world > 1 and not p.no_mirror:
         ent = _p2p_buffers(ra2.numel(), ra2.device, world, group)
     if ent is not None:
         n2 = ra2.numel()
@@ -110,6 +178,8 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
                       out={"rd": ent[0][:n2], "rid": ent[0][n2:2*n2].view(torch.int64)})
     else:
         res = compute(ra1_local, dec1_local, ra2, dec2, p)
+    if ready is not None:
+        torch.cuda.current_stream(ra1_local.device).wait_event(ready)      # later users of ra2 / dec2 on this stream
     mark("compute")
     ident, d, rid, rd = res.id, res.d, res.rid, res.rd
     if p.no_mirror:
@@ -117,14 +187,20 @@ def qxmatch_sharded(ra1_local, dec1_local, ra2, dec2, row_offset, params, group=
 
     rid = torch.as_tensor(rid).view(torch.int64) if not isinstance(rid, torch.Tensor) else rid
     rd = torch.as_tensor(rd) if not isinstance(rd, torch.Tensor) else rd
+    lo2, hi2 = shard_bounds(rid.numel(), world, rank)
     if rid.is_cuda:
-        merged = _merge_reverse_p2p(rid, rd, int(row_offset), bool(p.linear), world, group) if world > 1 else False
+        merged = _merge_reverse_p2p(rid, rd, int(row_offset), bool(p.linear), world, group,
+                                    replicate=replicate_reverse) if world > 1 else False
         if merged:
             rid, rd = merged
         else:
             _merge_reverse_cuda(rid, rd, int(row_offset), bool(p.linear), world, group)
+            if not replicate_reverse:
+                rid, rd = rid[lo2:hi2], rd[lo2:hi2]
     else:
         rid, rd = _merge_reverse_torch(rid, rd, int(row_offset), world, group)
+        if not replicate_reverse:
+            rid, rd = rid[lo2:hi2], rd[lo2:hi2]
     mark("merge")
     if timing and dist.get_rank(group) == 0:
         print("[qxmatch_sharded] " + " ".join("%s=%.3fms" % (marks[k][0], 1e3*(marks[k][1] - marks[k-1][1]))
@@ -480,12 +556,14 @@ _P2P_MAX = 4        # distinct catalog-2 sizes that get peer-mapped buffers (32 
 _P2P_OFF = set()    # groups on which symmetric memory could not be set up: NCCL merge from then on
 
 
-def _merge_reverse_p2p(rid, rd, row_offset, linear, world, group):
+def _merge_reverse_p2p(rid, rd, row_offset, linear, world, group, replicate=True):
     """Reverse merge as ONE kernel over NVLink peer memory (xm_rev_merge_p2p): every rank publishes
     its (rd, rid, first row) in a symmetric buffer, merges its slice of the rows straight out of its
     peers' memory and stores the result into every peer. torch's symmetric memory provides the peer
     mappings and the two device-side barriers. Returns (rid, rd), or False when symmetric memory is
-    unavailable (the caller falls back to the NCCL all-reduce merge); XM_MERGE=nccl forces that."""
+    unavailable (the caller falls back to the NCCL all-reduce merge); XM_MERGE=nccl forces that.
+    replicate=False: every rank keeps the rows it merged, [shard_bounds(n, world, rank)), and nothing is
+    stored into the peers."""
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -507,13 +585,19 @@ def _merge_reverse_p2p(rid, rd, row_offset, linear, world, group):
             exch[n:2*n].view(torch.int64).copy_(rid)
         exch[2*n:].view(torch.int64).fill_(row_offset)
         hx.barrier(channel=0)
-        rc = lib.xm_rev_merge_p2p(px, po, n, dist.get_rank(group), world, float("inf") if linear else float("nan"),
+        me = dist.get_rank(group)
+        if replicate:
+            pout = po
+        else:
+            pout = (C.c_void_p*world)(*[(po[q] if q == me else None) for q in range(world)])
+        rc = lib.xm_rev_merge_p2p(px, pout, n, me, world, float("inf") if linear else float("nan"),
                                   dev.index or 0, side.cuda_stream, err, 512)
         if rc != 0:
             raise RuntimeError(err.value.decode())
-        ho.barrier(channel=0)
-        res_rd = out[:n].clone()
-        res_rid = out[n:].view(torch.int64).clone()
+        ho.barrier(channel=0)      # every peer has read this rank's exchange buffer (and stored its rows here)
+        lo, hi = (0, n) if replicate else shard_bounds(n, world, me)
+        res_rd = out[lo:hi].clone()
+        res_rid = out[n + lo:n + hi].view(torch.int64).clone()
     cur.wait_stream(side)
     return res_rid, res_rd
 

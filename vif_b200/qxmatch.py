@@ -52,6 +52,8 @@ class QxmatchParams:
     exact_grid: bool = False   # brute_force result through the exact spherical grid search
     fwd_range: tuple = None    # (begin, count) of catalog-1 rows to match   } partitioned runs: both catalogs
     rev_range: tuple = None    # (begin, count) of catalog-2 rows to reverse  } whole, device path only
+    bbox2: tuple = None        # with bbox1: catalog 2's bounding box -> no host round trip at the head of the call
+    cat2_ready_event: int = 0  # cudaEvent_t handle: nothing reads catalog 2 before it (broadcast still in flight)
 
     def to_c(self):
         p = _lib.XmParams()
@@ -69,6 +71,12 @@ class QxmatchParams:
             p.has_bbox1 = 1
             for k in range(4):
                 p.bbox1[k] = float(self.bbox1[k])
+        if self.bbox2 is not None:
+            p.has_bbox2 = 1
+            for k in range(4):
+                p.bbox2[k] = float(self.bbox2[k])
+        if self.cat2_ready_event:
+            p.cat2_ready_event = int(self.cat2_ready_event)
         return p
 
 
