@@ -12,11 +12,18 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok_all = True
-for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 100_000, 120_000, dict(nth=3)),
+ONLY = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None      # optional subset of the cases
+
+
+def _sel(cases):
+    return [c for c in cases if ONLY is None or c[0] in ONLY]
+
+
+for name, n1, n2, kw in _sel((("binned", 300_000, 250_000, dict()), ("binned_nth3", 100_000, 120_000, dict(nth=3)),
                          ("brute", 20_000, 15_000, dict(brute_force=True)), ("nomirror", 50_000, 50_000, dict(no_mirror=True)),
                          ("ties_across_shards", 100_000, 80_000, dict()), ("binned_nccl_merge", 300_000, 250_000, dict()),
                          ("ties_nccl_merge", 100_000, 80_000, dict()), ("sparse_unmatched", 2_000, 50_000, dict()),
-                         ("fullsky", 400_000, 300_000, dict())):
+                         ("fullsky", 400_000, 300_000, dict()))):
     os.environ["XM_MERGE"] = "nccl" if name.endswith("nccl_merge") else "p2p"
     gen = G.fullsky if name == "fullsky" else G.c2
     full1 = gen(1, n1, xp="torch", device=dev)
@@ -58,8 +65,8 @@ for name, n1, n2, kw in (("binned", 300_000, 250_000, dict()), ("binned_nth3", 1
             ok_all &= bool(flag.item())
 # declination-band decomposition (qxmatch_banded): both directions sharded; must equal the single-GPU exact search
 from vif_b200.distributed import qxmatch_banded
-for name, n1, n2, halo in (("banded", 2_000_000, 1_000_000, None), ("banded_dups", 600_000, 500_000, None),
-                           ("banded_fallback", 300_000, 200_000, 0.002)):
+for name, n1, n2, halo in _sel((("banded", 2_000_000, 1_000_000, None), ("banded_dups", 600_000, 500_000, None),
+                                 ("banded_fallback", 300_000, 200_000, 0.002))):
     full1 = G.fullsky(1, n1, xp="torch", device=dev)
     full2 = G.fullsky(2, n2, xp="torch", device=dev)
     if name == "banded_dups":            # identical points inside and across the catalogs: ties go to the smallest row
@@ -90,7 +97,7 @@ for name, n1, n2, halo in (("banded", 2_000_000, 1_000_000, None), ("banded_dups
     ok_all &= bool(flag.item())
 # partitioned run (replicated catalogs, row blocks of both): must equal the single-GPU result
 from vif_b200.distributed import qxmatch_partitioned
-for name, n1, n2 in (("partitioned", 300_001, 250_003), ("partitioned_even", 200_000, 100_000)):
+for name, n1, n2 in _sel((("partitioned", 300_001, 250_003), ("partitioned_even", 200_000, 100_000))):
     full1 = G.c2(1, n1, xp="torch", device=dev)
     full2 = G.c2(2, n2, xp="torch", device=dev)
     lo, hi = shard_bounds(n1, world, rank)

@@ -382,8 +382,16 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
         for (int k = 0; k < 4; ++k) { bb1[k] = P.bbox1[k]; bb2[k] = P.bbox2[k]; }
     } else {
         if (cat2_ready) XM_CUDA_TRY(cudaStreamWaitEvent(s, cat2_ready, 0));
+        if (!same_cat) {
+            // the two passes are independent streams of loads: side by side on two streams they share the HBM
+            // bandwidth instead of each leaving a third of it unused (2 x 37 us -> 50 us on 1e7-row catalogs)
+            XM_CUDA_TRY(cudaEventRecord(ctx->sync_ev[0], s));
+            XM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->sync_ev[0], 0));
+            if ((rc = launch_bbox(ra2, dec2, n2, ctx->d_small + 5, ctx->stream2, err, &launches))) return rc;
+            XM_CUDA_TRY(cudaEventRecord(ctx->sync_ev[1], ctx->stream2));
+        }
         if ((rc = launch_bbox(ra1, dec1, n1, ctx->d_small, s, err, &launches))) return rc;
-        if (!same_cat && (rc = launch_bbox(ra2, dec2, n2, ctx->d_small + 5, s, err, &launches))) return rc;
+        if (!same_cat) XM_CUDA_TRY(cudaStreamWaitEvent(s, ctx->sync_ev[1], 0));
         XM_CUDA_TRY(cudaMemcpyAsync(ctx->h_small, ctx->d_small, 10*sizeof(unsigned long long),
                                     cudaMemcpyDeviceToHost, s));
         XM_CUDA_TRY(cudaEventRecord(ev[1], s));

@@ -33,8 +33,10 @@ __device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridVi
     const double fx = floor(__ddiv_rn(__dsub_rn(ra, g.rra0), g.dra));
     const double fy = floor(__ddiv_rn(__dsub_rn(dec, g.rdec0), g.ddec));
     if (on_grid) *on_grid = fx >= 0 && fx < (double)g.nra && fy >= 0 && fy < (double)g.ndec;     // false for NaN
-    const uint32_t ix = fx < 0 ? 0u : (fx >= (double)g.nra ? g.nra - 1 : (uint32_t)fx);
-    const uint32_t iy = fy < 0 ? 0u : (fy >= (double)g.ndec ? g.ndec - 1 : (uint32_t)fy);
+    // clamped onto the grid; written so that a NaN takes the first branch (a float -> integer conversion of NaN
+    // is not something to rely on)
+    const uint32_t ix = !(fx >= 0) ? 0u : (fx >= (double)g.nra ? g.nra - 1 : (uint32_t)fx);
+    const uint32_t iy = !(fy >= 0) ? 0u : (fy >= (double)g.ndec ? g.ndec - 1 : (uint32_t)fy);
     return ix*g.ndec + iy;
 }
 

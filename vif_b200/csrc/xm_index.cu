@@ -82,8 +82,8 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
     if (off_grid && !(fx >= 0 && fx < (double)nra && fy >= 0 && fy < (double)ndec)) atomicAdd(off_grid, 1ull);
     // with has_bbox1 a caller could hand us rows outside the box it promised: clamp instead of
     // writing out of bounds (rows inside the box are unaffected)
-    uint32_t ix = fx < 0 ? 0u : (fx >= (double)nra ? nra - 1 : (uint32_t)fx);
-    uint32_t iy = fy < 0 ? 0u : (fy >= (double)ndec ? ndec - 1 : (uint32_t)fy);
+    uint32_t ix = !(fx >= 0) ? 0u : (fx >= (double)nra ? nra - 1 : (uint32_t)fx);      // NaN -> 0
+    uint32_t iy = !(fy >= 0) ? 0u : (fy >= (double)ndec ? ndec - 1 : (uint32_t)fy);
     keys[i] = ix*ndec + iy;
     vals[i] = i;
 }

@@ -466,7 +466,7 @@ ring_nn32_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __rest
 #endif
 constexpr int kCons = XM_NN32_CONS, kProd = 256 - kCons, kPThreads = kCons + kProd;
 #ifndef XM_NN32_PB
-#define XM_NN32_PB 4
+#define XM_NN32_PB 3
 #endif
 constexpr int kPB = XM_NN32_PB;        // candidate records a producer thread keeps in flight
 constexpr int kSrcPer = (kCons + kProd - 1)/kProd;    // source records per producer thread
