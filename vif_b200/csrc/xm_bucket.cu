@@ -149,10 +149,11 @@ place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint
         bool on = true;
         key[k] = cell_key(r[k], d[k], g, &on);
         slot[k] = __ldg(cstart + key[k]) + rk[k];
-        if (!on) {
-            // a row that is not finite or off the grid (promised bounding boxes that did not hold: the call fails
-            // when it ends) is moved to the centre of the cell it was clamped to, so that every kernel downstream
-            // sees coordinates that agree with the index
+        if (!on && g.off_grid) {
+            // cell-binned path only (the spherical grid of xm_sphere.cu clamps its edge rows on purpose and passes no
+            // counter): a row that is not finite or off the grid (promised bounding boxes that did not hold: the call
+            // fails when it ends) is moved to the centre of the cell it was clamped to, so that every kernel
+            // downstream sees coordinates that agree with the index
             r[k] = g.rra0 + ((double)(key[k]/g.ndec) + 0.5)*g.dra;
             d[k] = g.rdec0 + ((double)(key[k]%g.ndec) + 0.5)*g.ddec;
         }

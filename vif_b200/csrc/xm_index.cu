@@ -92,15 +92,15 @@ keys_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint3
 __global__ void __launch_bounds__(kThreads)
 cells_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
                     const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n,
-                    int linear, int model, double rra0, double rdec0, double dra, double ddec, uint32_t nra,
-                    uint32_t ndec, Rec* __restrict__ rec) {
+                    int linear, int model, int sanitize, double rra0, double rdec0, double dra, double ddec,
+                    uint32_t nra, uint32_t ndec, Rec* __restrict__ rec) {
     const uint32_t p = blockIdx.x*blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t i = perm[p];
     double r = __ldg(ra + i), d = __ldg(dec + i);
     Rec out;
     out.idx = i; out.key = skeys[p];
-    {   // rows that are not finite or off the grid: to the centre of the cell they were clamped to (see place_kernel)
+    if (sanitize) {   // rows that are not finite or off the grid: to the centre of the cell they were clamped to (see place_kernel)
         const double fx = floor(__ddiv_rn(__dsub_rn(r, rra0), dra)), fy = floor(__ddiv_rn(__dsub_rn(d, rdec0), ddec));
         if (!(fx >= 0 && fx < (double)nra && fy >= 0 && fy < (double)ndec)) {
             r = rra0 + ((double)(out.key/ndec) + 0.5)*dra;
@@ -279,7 +279,7 @@ int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, con
                                 uint64_t* launches, int model, const GridView& g) {
     cell_offsets_kernel<<<(ncell + 1 + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, n, ncell, cstart);
     cells_gather_kernel<<<(n + kThreads - 1)/kThreads, kThreads, 0, s>>>(skeys, perm, ra, dec, n,
-                                                                        linear ? 1 : 0, model, g.rra0, g.rdec0, g.dra,
+                                                                        linear ? 1 : 0, model, g.off_grid ? 1 : 0, g.rra0, g.rdec0, g.dra,
                                                                         g.ddec, g.nra, g.ndec, rec);
     *launches += 2;
     XM_CUDA_TRY(cudaGetLastError());
