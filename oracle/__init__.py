@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY: loaders for the CPU oracle (port) and the compiled reference.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this package.
-Nothing under vif_b200/ does (checked by tests/test_no_oracle_in_product.py).
+Nothing under vif_b200/ or include/ does (checked by tests/test_abi.py::test_no_oracle_in_product).
 """
 from .oracle import (OracleGrid, have_ref, oracle_qxmatch, oracle_grid, oracle_ring,  # noqa: F401
                      oracle_field_area_bbox, oracle_angdist, ref_qxmatch, ref_ring,

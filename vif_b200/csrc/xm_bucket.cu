@@ -3,11 +3,10 @@
 // The reference pushes row ids into per-cell vectors in ascending row order. Rebuilt here as a
 // counting sort whose every pass streams (no random 8-byte gathers, only full-sector scatters):
 //   1. count:  one pass over (ra, dec): cell key (IEEE subtract/divide/floor as the reference),
-//              atomicAdd on the per-cell counter (the table is L2-resident); the returned value is
-//              kept as the row's arrival rank;
+//              atomic add on the per-cell counter (the table is L2-resident; a reduction: nothing returned);
 //   2. scan:   exclusive prefix sum of the counters -> CSR offsets cstart[ncell+1];
-//   3. place:  second pass over (ra, dec): slot = cstart[key] + the rank the counting atomic returned
-//              in pass 1; the source's 32-byte record (radians, cos(dec), row, key) is written to that slot -- a
+//   3. place:  second pass over (ra, dec): the slot is drawn from a cursor that starts as a copy of cstart
+//              (atomicAdd); the source's 32-byte record (radians, cos(dec), row, key) is written to that slot -- a
 //              scattered store of one full DRAM sector, no read-modify-write;
 //   4. order (skipped for nearest-neighbour-only calls, whose kernels do not depend on the order
 //              inside a cell):  atomics fill a cell in arbitrary order, the reference's order inside a cell is
@@ -41,35 +40,6 @@ __device__ __forceinline__ uint32_t cell_key(double ra, double dec, const GridVi
 }
 
 constexpr int kRows = 4;     // rows per thread: independent loads / atomics in flight
-
-// pass 1: per-cell counters; the value the atomic returns is the row's arrival rank in its cell
-__global__ void __launch_bounds__(kThreads)
-count_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
-             uint32_t* __restrict__ count, uint32_t* __restrict__ rank) {
-    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
-    double r[kRows], d[kRows];
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-        const uint32_t i = base + k*kThreads;
-        r[k] = i < n ? __ldg(ra + i) : 0.0;
-        d[k] = i < n ? __ldg(dec + i) : 0.0;
-    }
-    uint32_t rk[kRows];
-    uint32_t off = 0;
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-        const uint32_t i = base + k*kThreads;
-        bool on = true;
-        rk[k] = i < n ? atomicAdd(count + cell_key(r[k], d[k], g, &on), 1u) : 0u;
-        off += (i < n && !on) ? 1u : 0u;
-    }
-    if (off && g.off_grid) atomicAdd(g.off_grid, (unsigned long long)off);
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-        const uint32_t i = base + k*kThreads;
-        if (i < n) rank[i] = rk[k];
-    }
-}
 
 // ---- exclusive scan of u32 (three-level, in place) ------------------------------------------------
 constexpr int kScanThreads = 256;
@@ -129,26 +99,52 @@ void exclusive_scan(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, u
     }
 }
 
-// ---- placement --------------------------------------------------------------------------------------
-// pass 2: slot = cstart[key] + arrival rank; one full-sector store per source, no atomics
+// ---- count and placement --------------------------------------------------------------------------------------
+// pass 1: per-cell counters. The pass only adds (no value returned: a reduction, which does not hold the warp until
+// the atomic comes back; round 1 kept the returned value as the row's arrival rank: 98 us against 64 us per 1e7 rows).
 __global__ void __launch_bounds__(kThreads)
-place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
-             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ rank, Rec* __restrict__ out) {
+count_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+                 uint32_t* __restrict__ count) {
     const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
     double r[kRows], d[kRows];
-    uint32_t rk[kRows], key[kRows], slot[kRows];
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
         const uint32_t i = base + k*kThreads;
         r[k] = i < n ? __ldg(ra + i) : 0.0;
         d[k] = i < n ? __ldg(dec + i) : 0.0;
-        rk[k] = i < n ? __ldg(rank + i) : 0u;
+    }
+    uint32_t off = 0;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        if (i >= n) continue;
+        bool on = true;
+        atomicAdd(count + cell_key(r[k], d[k], g, &on), 1u);
+        off += on ? 0u : 1u;
+    }
+    if (off && g.off_grid) atomicAdd(g.off_grid, (unsigned long long)off);
+}
+
+// pass 2: the row's slot is drawn from a cursor that starts as a copy of the CSR offsets (atomicAdd, L2-resident);
+// one full-sector store per source
+__global__ void __launch_bounds__(kThreads)
+place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+             uint32_t* __restrict__ cursor, Rec* __restrict__ out) {
+    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
+    double r[kRows], d[kRows];
+    uint32_t key[kRows], slot[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        r[k] = i < n ? __ldg(ra + i) : 0.0;
+        d[k] = i < n ? __ldg(dec + i) : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
         bool on = true;
         key[k] = cell_key(r[k], d[k], g, &on);
-        slot[k] = __ldg(cstart + key[k]) + rk[k];
+        slot[k] = i < n ? atomicAdd(cursor + key[k], 1u) : 0u;
         if (!on && g.off_grid) {
             // cell-binned path only (the spherical grid of xm_sphere.cu clamps its edge rows on purpose and passes no
             // counter): a row that is not finite or off the grid (promised bounding boxes that did not hold: the call
@@ -259,19 +255,20 @@ size_t bucket_scan_aux_bytes(uint32_t ncell) {
 }
 
 // rec_out: n records; rec_tmp: n records (only touched when order_cells); cstart: ncell+1 words;
-// rank: n words; aux: bucket_scan_aux_bytes(ncell). order_cells = false leaves every cell in
+// cursor: ncell words; aux: bucket_scan_aux_bytes(ncell). order_cells = false leaves every cell in
 // arrival order (callers that do not depend on the order inside a cell skip a full pass);
 // *overflow (device word) is incremented when a cell was too large to order.
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
                             uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
-                            uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
+                            uint32_t* cstart, uint32_t* cursor, uint32_t* aux, uint32_t* overflow,
                             cudaStream_t s, Error& err, uint64_t* launches) {
     XM_CUDA_TRY(cudaMemsetAsync(cstart, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
     const uint32_t blocks = (n + kThreads*kRows - 1)/(kThreads*kRows);
-    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank);
+    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart);
     *launches += 1;
     exclusive_scan(cstart, ncell + 1, aux, s, launches);
-    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank, order_cells ? rec_tmp : rec_out);
+    XM_CUDA_TRY(cudaMemcpyAsync(cursor, cstart, (size_t)ncell*sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cursor, order_cells ? rec_tmp : rec_out);
     *launches += 1;
     if (order_cells) {
         const uint64_t threads = (uint64_t)ncell*32;

@@ -131,7 +131,7 @@ size_t  bucket_scan_aux_bytes(uint32_t ncell);
 void    launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches);
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
                             uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
-                            uint32_t* cstart, uint32_t* rank, uint32_t* aux, uint32_t* overflow,
+                            uint32_t* cstart, uint32_t* cursor, uint32_t* aux, uint32_t* overflow,
                             cudaStream_t s, Error& err, uint64_t* launches);
 size_t  clean_best_scratch_bytes(uint32_t n1);
 int32_t launch_clean_best(const uint64_t* id, const uint64_t* rid, uint32_t n1, uint64_t n2, uint64_t* id1,
