@@ -601,9 +601,27 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             if ((rc = launch_fill_outputs(id, d, nth*n1o, linear ? dinf : dnan, s, err, &launches))) return rc;
         }
         // ---- forward search (lane s) ----
-        bool timed_f = false, timed_r = false;
+        bool timed_f = false, timed_r = false, fwd_deferred = false;
         int tile_f = 0;
         Scratch refine, resrec, plans;
+        // what follows the forward filter: (unpack, when deferred) || exact kernel of the undecided rows on a side
+        // stream -> join
+        auto fwd_post = [&]() -> int32_t {
+            if (fwd_deferred) {
+                XM_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_ev[2], 0));             // the reverse filter has run
+                int32_t r = launch_unpack_results(resrec.p, srcF->n, id, d, s, err, &launches);
+                if (r) return r;
+                XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[0], ctx->lane_ev[2], 0));
+            }
+            XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[0], ctx->lane_ev[0], 0));
+            int32_t r = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
+                                                 (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr,
+                                                 ctx->side[0], err, &launches);
+            if (r) return r;
+            XM_CUDA_TRY(cudaEventRecord(ctx->lane_ev[1], ctx->side[0]));
+            XM_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_ev[1], 0));
+            return XM_OK;
+        };
         if (srcF->n == 0) {
             // empty block: nothing to match
         } else if (fast && nth_eff == 1) {
@@ -613,9 +631,17 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             const int tile = filter_v1 ? 0 : nn32_tile_sources(g, srcF->n, v2->n);
             if (tile) {
                 XM_CUDA_TRY(plans.alloc(nn32_plan_bytes(n1o, g.nra, tile), s));
+                // Device-resident results, both directions through the persistent filter: the forward lane's unpack
+                // pass and exact list wait until the reverse filter has run. Beside it they cost it 0.13 ms (0.64
+                // against 0.50 ms per launch) -- more than they take themselves -- while after it they overlap with the
+                // reverse lane's own unpack pass. With host outputs the order stays: the forward results must leave
+                // for the host as early as possible. XM_NN32_NODEFER=1 keeps the round-1 order.
+                fwd_deferred = !ctx->host_out.id && mirror && n2o && !self && tile == nn32_persistent_tile() &&
+                               nn32_tile_sources(g, srcR->n, s1.view.n) == tile && !getenv("XM_NN32_NODEFER") &&
+                               !getenv("XM_NN32_CONCURRENT");
                 if ((rc = launch_ring_nn32(g, *srcF, *v2, self, tile, id, d, resrec.p, plans.p, refine.as<uint32_t>(),
                                            &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
-                                           &launches, ctx->kev[0], ctx->kev[1]))) return rc;
+                                           &launches, ctx->kev[0], ctx->kev[1], nullptr, fwd_deferred))) return rc;
                 timed_f = true;
                 tile_f = tile;
             } else {
@@ -624,12 +650,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                                 &ctx->d_ctr->refine_fwd, false, ctx->d_ctr, s, ctx->lane_ev[0], err,
                                                 &launches))) return rc;
             }
-            XM_CUDA_TRY(cudaStreamWaitEvent(ctx->side[0], ctx->lane_ev[0], 0));
-            if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, 1u, n1o, id, d, refine.as<uint32_t>(),
-                                               (uint32_t)n1o, &ctx->d_ctr->refine_fwd, false, unordered, ctx->d_ctr,
-                                               ctx->side[0], err, &launches))) return rc;
-            XM_CUDA_TRY(cudaEventRecord(ctx->lane_ev[1], ctx->side[0]));
-            XM_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_ev[1], 0));
+            if (!fwd_deferred && (rc = fwd_post())) return rc;
         } else if (!P.exact_only && fast_path_applicable(g) && topk_filter_applicable(nth_eff)) {
             // nth = 2..8: top-K filter kernel, exact kernel on the rows it flags (cells are in row order)
             XM_CUDA_TRY(refine.alloc((size_t)n1o*4, s));
@@ -642,7 +663,7 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
             if ((rc = launch_ring_search_exact(g, *srcF, *v2, self_mode, nth_eff, n1o, id, d, nullptr,
                                                (uint32_t)n1o, nullptr, false, false, ctx->d_ctr, s, err, &launches))) return rc;
         }
-        XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+        if (!fwd_deferred) XM_CUDA_TRY(cudaEventRecord(ev[6], s));
         Context::HostOut& ho = ctx->host_out;
         if (ho.id) {
             XM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ev[6], 0));
@@ -665,6 +686,10 @@ int32_t run_device_once(Context* ctx, cudaStream_t s, const double* ra1, const d
                                                    s2, ctx->lane_ev[2], err, &launches, ctx->kev[2], ctx->kev[3],
                                                    (timed_f && tile_f == tile && !getenv("XM_NN32_CONCURRENT")) ? ctx->kev[1] : nullptr))) return rc;
                         timed_r = true;
+                        if (fwd_deferred) {
+                            if ((rc = fwd_post())) return rc;
+                            XM_CUDA_TRY(cudaEventRecord(ev[6], s));
+                        }
                     } else {
                         XM_CUDA_TRY(plans2.alloc(filter_plan_bytes(n2o), s2));
                         if ((rc = launch_ring_nn_filter(g, *srcR, s1.view, false, rid, rd, resrec2.p, plans2.p,

@@ -169,7 +169,8 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
                          uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                          SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
                          uint64_t* launches, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr,
-                         cudaEvent_t after = nullptr);
+                         cudaEvent_t after = nullptr, bool defer_unpack = false);
+int     nn32_persistent_tile();          // tile size served by the persistent form of the kernel (0: switched off)
 int32_t launch_ring_nn_filter(const GridView& g, const CatView& src, const CatView& cand, bool self,
                               uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                               uint32_t* refine_list, unsigned long long* refine_count, bool reverse,

@@ -761,6 +761,11 @@ int nn32_tile_sources(const GridView& g, uint64_t n_src, uint64_t n_cand) {
     return 0;
 }
 
+int nn32_persistent_tile() {
+    const char* pe = getenv("XM_NN32_PERSIST");
+    return (pe && pe[0] == '0') ? 0 : kCons;
+}
+
 size_t nn32_plan_bytes(uint64_t n_src, uint32_t nra, int tile) {
     const uint64_t ntiles = n_src/(uint64_t)tile + nra + 1;
     return (size_t)ntiles*sizeof(TilePlan32) + ((size_t)nra + 2)*sizeof(uint32_t) + bucket_scan_aux_bytes(nra + 1) + 64;
@@ -770,7 +775,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
                          uint64_t* id_out, double* d_out, void* result_scratch, void* plan_scratch,
                          uint32_t* refine_list, unsigned long long* refine_count, bool reverse,
                          SearchCounters* ctr, cudaStream_t s, cudaEvent_t filter_done, Error& err,
-                         uint64_t* launches, cudaEvent_t k0, cudaEvent_t k1, cudaEvent_t after) {
+                         uint64_t* launches, cudaEvent_t k0, cudaEvent_t k1, cudaEvent_t after, bool defer_unpack) {
     if (src.n == 0) return XM_OK;
     const uint32_t ntiles = src.n/(uint32_t)tile + g.nra + 1;
     TilePlan32* plan = (TilePlan32*)plan_scratch;
@@ -781,8 +786,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
     *launches += 1;
     launch_exclusive_scan_u32(toff, g.nra + 1, aux, s, launches);
     plan_tiles32_kernel<<<(ntiles + 255)/256, 256, 0, s>>>(g, src, cand, toff, (uint32_t)tile, ntiles, plan);
-    const char* pe = getenv("XM_NN32_PERSIST");
-    if (tile == kCons && !(pe && pe[0] == '0')) {
+    if (tile == nn32_persistent_tile()) {
         // persistent, warp-specialised form: 4 CTAs per SM for the whole launch
         int dev = 0, sms = 148;
         XM_CUDA_TRY(cudaGetDevice(&dev));
@@ -802,6 +806,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
         *launches += 2;
         if (k1) XM_CUDA_TRY(cudaEventRecord(k1, s));
         if (filter_done) XM_CUDA_TRY(cudaEventRecord(filter_done, s));
+        if (defer_unpack) { XM_CUDA_TRY(cudaGetLastError()); return XM_OK; }      // the caller unpacks later
         int32_t rcp = launch_unpack_results(result_scratch, src.n, id_out, d_out, s, err, launches);
         if (rcp) return rcp;
         XM_CUDA_TRY(cudaGetLastError());
