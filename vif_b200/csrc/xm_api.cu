@@ -214,7 +214,7 @@ int32_t build_index(const double* ra, const double* dec, uint32_t n, const GridV
     } else if (use_bucket) {
         Scratch tmp, cursor, aux;
         if (order_cells) XM_CUDA_TRY(tmp.alloc((size_t)n*sizeof(Rec), s));
-        XM_CUDA_TRY(cursor.alloc(((size_t)ncell + 1)*sizeof(uint32_t), s));
+        XM_CUDA_TRY(cursor.alloc(bucket_index_scratch_words(n, ncell)*sizeof(uint32_t), s));
         XM_CUDA_TRY(aux.alloc(bucket_scan_aux_bytes(ncell), s));
         rc = launch_bucket_index(ra, dec, n, g, ncell, order_cells, tmp.as<Rec>(), out.rec.as<Rec>(),
                                  out.cell.as<uint32_t>(), cursor.as<uint32_t>(), aux.as<uint32_t>(), overflow, s,

@@ -14,6 +14,8 @@
 //              row and writes them to their final slots (out of place, both sides streamed).
 // Cells holding more than kMaxCellSort rows are left unordered and reported through *overflow; the
 // caller then rebuilds that catalog with the stable radix sort (xm_sort.cu), which has no such limit.
+#include <cstdlib>
+
 #include "xm_common.cuh"
 #include "xm_math_exact.cuh"
 
@@ -167,6 +169,76 @@ place_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint
     }
 }
 
+// ---- the same two passes for cell tables that do not fit the L2 cache ---------------------------------------------
+// (the spherical grid of a 1e9-row catalog has 1e8 cells: a returning atomic on a DRAM-resident cursor costs more than
+// the plain read of cstart[key] it replaces, and the cursor is another 4 bytes per cell to copy: C5 on one GPU
+// 174 -> 181 ms with the cursor form). Here the counting atomic's return value is kept as the row's arrival rank and
+// the placement needs no atomic.
+__global__ void __launch_bounds__(kThreads)
+count_rank_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+             uint32_t* __restrict__ count, uint32_t* __restrict__ rank) {
+    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
+    double r[kRows], d[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        r[k] = i < n ? __ldg(ra + i) : 0.0;
+        d[k] = i < n ? __ldg(dec + i) : 0.0;
+    }
+    uint32_t rk[kRows];
+    uint32_t off = 0;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        bool on = true;
+        rk[k] = i < n ? atomicAdd(count + cell_key(r[k], d[k], g, &on), 1u) : 0u;
+        off += (i < n && !on) ? 1u : 0u;
+    }
+    if (off && g.off_grid) atomicAdd(g.off_grid, (unsigned long long)off);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        if (i < n) rank[i] = rk[k];
+    }
+}
+
+// pass 2: slot = cstart[key] + arrival rank; one full-sector store per source, no atomics
+__global__ void __launch_bounds__(kThreads)
+place_rank_kernel(const double* __restrict__ ra, const double* __restrict__ dec, uint32_t n, GridView g,
+             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ rank, Rec* __restrict__ out) {
+    const uint32_t base = blockIdx.x*(kThreads*kRows) + threadIdx.x;
+    double r[kRows], d[kRows];
+    uint32_t rk[kRows], key[kRows], slot[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        r[k] = i < n ? __ldg(ra + i) : 0.0;
+        d[k] = i < n ? __ldg(dec + i) : 0.0;
+        rk[k] = i < n ? __ldg(rank + i) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        bool on = true;
+        key[k] = cell_key(r[k], d[k], g, &on);
+        slot[k] = __ldg(cstart + key[k]) + rk[k];
+        if (!on && g.off_grid) {           // cell-binned path only: see place_kernel
+            r[k] = g.rra0 + ((double)(key[k]/g.ndec) + 0.5)*g.dra;
+            d[k] = g.rdec0 + ((double)(key[k]%g.ndec) + 0.5)*g.ddec;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const uint32_t i = base + k*kThreads;
+        if (i >= n) continue;
+        double x, y, c;
+        if (g.linear) { x = r[k]; y = d[k]; c = 1.0; }
+        else { y = __dmul_rn(d[k], XM_D2R); x = __dmul_rn(r[k], XM_D2R); c = cos_ref(y, g.sin_model); }   // qxmatch.hpp:174-180
+        const unsigned long long w = (unsigned long long)i | ((unsigned long long)key[k] << 32);
+        asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" :: "l"(out + slot[k]), "l"(__double_as_longlong(x)),
+                     "l"(__double_as_longlong(y)), "l"(__double_as_longlong(c)), "l"(w) : "memory");
+    }
+}
+
 // one warp per cell: rank the cell's records by original row, write them to their final slots
 __global__ void __launch_bounds__(kThreads)
 order_cells_kernel(const Rec* __restrict__ in, const uint32_t* __restrict__ cstart, uint32_t ncell,
@@ -254,8 +326,20 @@ size_t bucket_scan_aux_bytes(uint32_t ncell) {
     return (size_t)tot*sizeof(uint32_t);
 }
 
+// Cell tables beyond 2^24 cells (64 MB) take the rank form of the two passes (XM_INDEX_RANK=0 / 1 forces the cursor /
+// the rank form).
+bool bucket_index_uses_rank(uint32_t ncell) {
+    if (const char* e = getenv("XM_INDEX_RANK")) return e[0] == '1';
+    return ncell > (1u << 24);
+}
+
+// words of the `cursor` scratch: the cursor (one per cell) or the arrival ranks (one per row)
+size_t bucket_index_scratch_words(uint32_t n, uint32_t ncell) {
+    return bucket_index_uses_rank(ncell) ? (size_t)n : (size_t)ncell + 1;
+}
+
 // rec_out: n records; rec_tmp: n records (only touched when order_cells); cstart: ncell+1 words;
-// cursor: ncell words; aux: bucket_scan_aux_bytes(ncell). order_cells = false leaves every cell in
+// cursor: bucket_index_scratch_words(n, ncell) words; aux: bucket_scan_aux_bytes(ncell). order_cells = false leaves every cell in
 // arrival order (callers that do not depend on the order inside a cell skip a full pass);
 // *overflow (device word) is incremented when a cell was too large to order.
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
@@ -264,12 +348,21 @@ int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, con
                             cudaStream_t s, Error& err, uint64_t* launches) {
     XM_CUDA_TRY(cudaMemsetAsync(cstart, 0, ((size_t)ncell + 1)*sizeof(uint32_t), s));
     const uint32_t blocks = (n + kThreads*kRows - 1)/(kThreads*kRows);
-    count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart);
-    *launches += 1;
-    exclusive_scan(cstart, ncell + 1, aux, s, launches);
-    XM_CUDA_TRY(cudaMemcpyAsync(cursor, cstart, (size_t)ncell*sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cursor, order_cells ? rec_tmp : rec_out);
-    *launches += 1;
+    if (bucket_index_uses_rank(ncell)) {
+        uint32_t* rank = cursor;                 // n words (see bucket_index_scratch_words)
+        count_rank_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank);
+        *launches += 1;
+        exclusive_scan(cstart, ncell + 1, aux, s, launches);
+        place_rank_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart, rank, order_cells ? rec_tmp : rec_out);
+        *launches += 1;
+    } else {
+        count_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cstart);
+        *launches += 1;
+        exclusive_scan(cstart, ncell + 1, aux, s, launches);
+        XM_CUDA_TRY(cudaMemcpyAsync(cursor, cstart, (size_t)ncell*sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        place_kernel<<<blocks, kThreads, 0, s>>>(ra, dec, n, g, cursor, order_cells ? rec_tmp : rec_out);
+        *launches += 1;
+    }
     if (order_cells) {
         const uint64_t threads = (uint64_t)ncell*32;
         order_cells_kernel<<<(unsigned)((threads + kThreads - 1)/kThreads), kThreads, 0, s>>>(rec_tmp, cstart, ncell,

@@ -128,6 +128,8 @@ int32_t launch_cells_and_gather(const uint32_t* skeys, const uint32_t* perm, con
                                 uint64_t* launches, int model, const GridView& g);
 // xm_bucket.cu: counting-sort index (count -> scan -> place -> order cells); fast path
 size_t  bucket_scan_aux_bytes(uint32_t ncell);
+bool    bucket_index_uses_rank(uint32_t ncell);
+size_t  bucket_index_scratch_words(uint32_t n, uint32_t ncell);
 void    launch_exclusive_scan_u32(uint32_t* data, uint32_t n, uint32_t* aux, cudaStream_t s, uint64_t* launches);
 int32_t launch_bucket_index(const double* ra, const double* dec, uint32_t n, const GridView& g,
                             uint32_t ncell, bool order_cells, Rec* rec_tmp, Rec* rec_out,
