@@ -54,22 +54,30 @@ def _worker(rank, world, port, kw, out_dir):
     a1s, b1s = a1[lo:hi].copy(), b1[lo:hi].copy()
     ra2 = torch.from_numpy(a2.copy()) if rank == 0 else torch.zeros(n2, dtype=torch.float64)
     dec2 = torch.from_numpy(b2.copy()) if rank == 0 else torch.zeros(n2, dtype=torch.float64)
+    kw = dict(kw)
+    sliced = kw.pop("sliced", False)
     ident, d, rid, rd = qxmatch_sharded(torch.from_numpy(a1s), torch.from_numpy(b1s), ra2, dec2, lo,
-                                        QxmatchParams(**kw), compute=_oracle_compute, bbox=_bbox)
+                                        QxmatchParams(**kw), compute=_oracle_compute, bbox=_bbox,
+                                        replicate_reverse=not sliced)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), id=ident.numpy(), d=d.numpy(), rid=rid.numpy(), rd=rd.numpy(),
              lo=lo, hi=hi)
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world,kw", [(2, dict(brute_force=True)), (3, dict(brute_force=True, nth=2)),
-                                      (2, dict(brute_force=True, no_mirror=True))],
-                         ids=["w2", "w3_nth2", "w2_nomirror"])
+                                      (2, dict(brute_force=True, no_mirror=True)),
+                                      (3, dict(brute_force=True, sliced=True))],
+                         ids=["w2", "w3_nth2", "w2_nomirror", "w3_sliced"])
 def test_sharded_equals_single(tmp_path, oracle, world, kw):
     """brute force is used so that each shard's result is independent of the grid; the merged
-    reverse match must equal the single-process one, ties included (smallest global row id)."""
+    reverse match must equal the single-process one, ties included (smallest global row id).
+    sliced: replicate_reverse=False leaves every rank with the merged rows of its catalog-2 row block."""
     from vif_b200 import catalogs as G
+    from vif_b200.distributed import shard_bounds
     port = _free_port()
     mp.spawn(_worker, args=(world, port, kw, str(tmp_path)), nprocs=world, join=True)
+    kw = dict(kw)
+    sliced = kw.pop("sliced", False)
     n1, n2 = 3000, 2500
     a1, b1 = G.c1(41, n1)
     a2, b2 = G.c1(42, n2)
@@ -79,8 +87,9 @@ def test_sharded_equals_single(tmp_path, oracle, world, kw):
         z = np.load(tmp_path / f"r{r}.npz")
         ids.append(z["id"]); ds.append(z["d"])
         if not kw.get("no_mirror"):
-            assert np.array_equal(z["rid"].view(np.uint64), exp["rid"])
-            assert np.array_equal(z["rd"], exp["rd"], equal_nan=True)
+            lo2, hi2 = shard_bounds(n2, world, r) if sliced else (0, n2)
+            assert np.array_equal(z["rid"].view(np.uint64), exp["rid"][lo2:hi2])
+            assert np.array_equal(z["rd"], exp["rd"][lo2:hi2], equal_nan=True)
     assert np.array_equal(np.concatenate(ids, axis=1).view(np.uint64), exp["id"])
     assert np.array_equal(np.concatenate(ds, axis=1), exp["d"], equal_nan=True)
 

@@ -491,8 +491,13 @@ struct __align__(16) Persist32 {
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 
+#ifndef XM_NN32_PCTAS
+#define XM_NN32_PCTAS 4
+#endif
+constexpr int kPCtas = XM_NN32_PCTAS;  // persistent CTAs per SM (register-bound: 4 x 256 threads x 64 registers)
+
 template <bool SELF, bool PF>
-__global__ void __launch_bounds__(kPThreads, 4)
+__global__ void __launch_bounds__(kPThreads, kPCtas)
 ring_nn32p_kernel(GridView g, CatView src, CatView cand, const TilePlan32* __restrict__ plan,
                   const uint32_t* __restrict__ ntiles_dev, ResRec* __restrict__ res,
                   uint32_t* __restrict__ refine_list, unsigned long long* refine_count, int reverse,
@@ -791,7 +796,7 @@ int32_t launch_ring_nn32(const GridView& g, const CatView& src, const CatView& c
         int dev = 0, sms = 148;
         XM_CUDA_TRY(cudaGetDevice(&dev));
         XM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const uint32_t grid = (uint32_t)sms*4u < ntiles ? (uint32_t)sms*4u : ntiles;
+        const uint32_t grid = (uint32_t)(sms*kPCtas) < ntiles ? (uint32_t)(sms*kPCtas) : ntiles;
         // XM_NN32_PF=1: with the L2 prefetch of the next tile's records (measured: see DESIGN.md 4.2)
         static const bool pf = [] { const char* e = getenv("XM_NN32_PF"); return e && e[0] == '1'; }();
         auto kern = self ? (pf ? ring_nn32p_kernel<true, true> : ring_nn32p_kernel<true, false>)
