@@ -509,6 +509,26 @@ def test_promised_boxes_and_late_catalog2(kw):
     assert torch.equal(again.id, whole.id)
 
 
+def test_bbox_neg_dev_feeds_one_allreduce():
+    """xm_bbox_neg_dev leaves {-min ra, max ra, -min dec, max dec, bad rows} on the device, on the caller's stream,
+    without a host round trip: the operand of the single all-reduce(max) of the row-sharded step
+    (qxmatch.hpp:232-238 over shards). An empty shard is the neutral element."""
+    from vif_b200.distributed import _cuda_bbox_neg
+    ra, dec = [torch.from_numpy(x).cuda() for x in G.c2(93, 200_003)]
+    ra[17] = float("nan"); dec[99] = float("inf")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = torch.full((10,), 7.0, dtype=torch.float64, device="cuda")
+        _cuda_bbox_neg(ra, dec, out[0:5])
+        _cuda_bbox_neg(ra[:0], dec[:0], out[5:10])
+        got = out.tolist()
+    ok = torch.isfinite(ra) & torch.isfinite(dec)
+    exp = [-float(ra[ok].min()), float(ra[ok].max()), -float(dec[ok].min()), float(dec[ok].max()), 2.0]
+    assert got[0:5] == exp
+    assert got[5:9] == [float("-inf")] * 4 and got[9] == 0.0
+
+
 # ---- the FP64 filter kernel against its numpy model (tests/ring_filter_model.py) ----------------------------
 @pytest.mark.parametrize("name", ["c1_box", "tall_dec_field", "high_dec_box", "displaced_copies", "large_cells", "self"])
 def test_fp64_filter_flags_the_rows_its_model_flags(oracle, name, monkeypatch):
