@@ -78,6 +78,26 @@ def test_ring_enumeration_matches_reference_tables(dedupe):
     assert checked > 50
 
 
+def test_depth_one_is_the_whole_5x5_block():
+    """The FP32 filter (xm_search_nn32.cu, ring0_decide) evaluates no stop rule after ring 1: it relies on depth 1
+    of the reference's table (qxmatch.hpp:44-128: the first grow() runs with d = 2, max_dist = 2.5 cell sizes) being
+    every cell of the 5x5 block but the centre, so that a source whose masked neighbours and 16 outer cells are
+    accounted for has seen everything the reference sees before its second stop test. Checked on the reference's
+    own dumped tables and on the library's closed form."""
+    lib = _lib.load()
+    block = {(x, y) for x in range(-2, 3) for y in range(-2, 3)} - {(0, 0)}
+    for nx, ny in GEO["grids"]:
+        if min(nx, ny) < 5:
+            continue
+        bx, by = GEO[f"ring_{nx}_{ny}_1_bx"], GEO[f"ring_{nx}_{ny}_1_by"]
+        assert set(zip(bx.tolist(), by.tolist())) == block, (nx, ny)
+        assert set(zip(GEO[f"ring_{nx}_{ny}_0_bx"].tolist(), GEO[f"ring_{nx}_{ny}_0_by"].tolist())) == {(0, 0)}
+    cap = 64
+    gx, gy = (C.c_int32 * cap)(), (C.c_int32 * cap)()
+    n = lib.xm_ring_entries(1, 890, 890, 1, gx, gy, cap)
+    assert n == 24 and set(zip(gx[:n], gy[:n])) == block
+
+
 def test_ring_counts():
     lib = _lib.load()
     n = [lib.xm_ring_entries(k, 91, 91, 0, None, None, 0) for k in range(4)]
